@@ -1,0 +1,32 @@
+"""html5-canvas-raytracer_b200 — B200-native replacement for the per-pixel hot path of
+termuxinator/html5-canvas-raytracer's main.js, behind the reference-shaped host interface.
+
+The directory name carries hyphens (it is the name the build contract fixes), so import it with
+`importlib.import_module("html5-canvas-raytracer_b200")` or through the root-level alias `rtb200`.
+
+Layout: csrc/ (CUDA kernels + C ABI, built to csrc/librtb200.so), scene.py (mirror of main.js's
+constructors), scenes.py (BASELINE.json workloads), render.py (Renderer: the redraw() replacement),
+multigpu.py (row-stripe / frame-batch sharding over torch.distributed + NCCL).
+"""
+from . import _abi
+from ._abi import (RTB_CAMERA_BASIS, RTB_CAMERA_REFERENCE, RTB_KERNEL_AUTO, RTB_KERNEL_PIXEL,
+                   RTB_KERNEL_WAVEFRONT, RTB_PRECISION_FP32, RTB_PRECISION_FP64, RTB_STARS_HASH,
+                   RTB_STARS_OFF, RtbError)
+from .scene import (Camera, Material, SceneDesc, Sphere, Texture, checkerSampler, checkerTexture,
+                    colorSampler, createMaterial, createSphere, createTexture, loadTexture, make_opts,
+                    sortObjects, starSampler, textureFromRGBA, textureSampler)
+from . import scenes
+
+__all__ = [n for n in dir() if not n.startswith("__")]
+
+
+def __getattr__(name):
+    # Renderer and the multi-GPU layer need the CUDA library / torch; import them lazily so that
+    # scene construction (and the CPU test-suite) works on a box without a GPU.
+    if name in ("Renderer", "render"):
+        from . import render as _r
+        return getattr(_r, name) if name == "Renderer" else _r
+    if name == "multigpu":
+        from . import multigpu as _m
+        return _m
+    raise AttributeError(name)

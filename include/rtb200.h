@@ -1,0 +1,210 @@
+/*
+ * rtb200.h — C ABI of the B200-native replacement for the per-pixel hot path of
+ * termuxinator/html5-canvas-raytracer (reference: main.js, build '741').
+ *
+ * The reference exports nothing (main.js is a module script without `export`); the replaceable
+ * unit is the body of the row/column loops of `spanish(y)` (main.js:183-199), whose only
+ * observable effect is filling `colorbuf.data` (a Uint8ClampedArray(W*H*4), main.js:83) before
+ * `context.putImageData` (main.js:200).  Everything that loop captures from `main()`'s closure
+ * becomes an explicit field below; closures (`mtl.sampler`) become enumerated sampler kinds.
+ *
+ * Ownership : the caller owns every pointer it passes and the output buffer; the library copies
+ *             what it needs during the call and keeps no caller pointer.
+ * Errors    : 0 = RTB_OK, negative = error; message via rtb_last_error() (thread-local).
+ *             The library never aborts and never throws across this boundary.
+ * Threading : synchronous; one render in flight per scene handle (the reference's caller is the
+ *             single JS thread).  CUDA streams are library-owned.
+ * No CPU fallback: every entry point that computes needs a CUDA device and fails with
+ *             RTB_ERR_NO_DEVICE / RTB_ERR_CUDA otherwise.
+ *
+ * Plain C, no CUDA/torch types: this header is what a cgo / ctypes / N-API binding includes.
+ */
+#ifndef RTB200_H
+#define RTB200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RTB_ABI_VERSION 1u
+#define RTB_MAX_LIGHTS 4      /* main.js:283 lists 2 live + 2 commented-out lights */
+#define RTB_MAX_SEGS 16       /* recursion depth literal is 8 at main.js:194 */
+
+/* ---- error codes --------------------------------------------------------------------------- */
+enum {
+  RTB_OK = 0,
+  RTB_ERR_INVALID = -1,        /* bad argument / malformed scene (message says which field)      */
+  RTB_ERR_NO_DEVICE = -2,      /* no CUDA device visible — there is no CPU fallback              */
+  RTB_ERR_CUDA = -3,           /* a CUDA runtime call failed (message carries cudaGetErrorString) */
+  RTB_ERR_OOM = -4,            /* device or host allocation failed                               */
+  RTB_ERR_NOT_INIT = -5,       /* rtb_init() not called                                          */
+  RTB_ERR_OVERFLOW = -6,       /* internal ray queue overflow that band splitting could not fix  */
+  RTB_ERR_UNSUPPORTED = -7     /* valid request this build does not implement                    */
+};
+
+/* ---- sampler kinds: what `mtl.sampler(hit)` (main.js:320) was at scene-build time ------------ */
+enum {
+  RTB_SAMPLER_COLOR = 0,    /* default `return hit.m.color`            main.js:404              */
+  RTB_SAMPLER_TEXTURE = 1,  /* `sampleTexture(unit, hit.u, hit.v)`     main.js:143-157, 343-351 */
+  RTB_SAMPLER_CHECKER = 2,  /* home-sphere procedural checker on hit.n main.js:126-133          */
+  RTB_SAMPLER_STARS = 3     /* skybox `Math.random()` stars            main.js:135-139          */
+};
+
+/* ---- precision / kernel selection ------------------------------------------------------------ */
+enum {
+  RTB_PRECISION_FP32 = 0,   /* throughput kernels (graded: +-2 LSB on >= 99.9 % of pixels)       */
+  RTB_PRECISION_FP64 = 1    /* validation kernel, reference operation order, no FMA contraction  */
+};
+enum {
+  RTB_KERNEL_AUTO = 0,      /* fp64 -> per-pixel kernel; fp32 -> wavefront                       */
+  RTB_KERNEL_PIXEL = 1,     /* one thread per pixel, explicit post-order stack                   */
+  RTB_KERNEL_WAVEFRONT = 2  /* fp32 only: ballot-compacted ray queues per recursion level        */
+};
+enum {
+  RTB_STARS_OFF = 0,        /* Math.random() stubbed to a constant >= threshold: sky is black    */
+  RTB_STARS_HASH = 1        /* deterministic per-(pixel,node) counter hash in place of Math.random;
+                               NOT the reference's raster-order stream       */
+};
+enum {
+  RTB_CAMERA_REFERENCE = 0, /* main.js:187-191 verbatim: per-COMPONENT dist (bug-compatible)     */
+  RTB_CAMERA_BASIS = 1      /* target = origin + axisX*dist[0] + axisY*dist[1] + axisZ*dist[2]   */
+};
+
+/* ---- scene description ----------------------------------------------------------------------- */
+
+/* createMaterial(color, albedo, se, ri) main.js:397-406, plus the sampler closure as a kind. */
+typedef struct RtbMaterial {
+  double color[3];
+  double albedo[5];            /* ambient, diffuse, specular, reflect, refract (main.js:400)      */
+  double specular_exponent;
+  double refract_index;
+  int32_t sampler_kind;        /* RTB_SAMPLER_*                                                  */
+  int32_t texture_unit;        /* RTB_SAMPLER_TEXTURE: index into RtbSceneDesc.textures          */
+  double checker_freq[2];      /* RTB_SAMPLER_CHECKER: 5000, 2500 (main.js:129-130)              */
+  double checker_color[2][3];  /* RTB_SAMPLER_CHECKER: [1,1,0],[1,0,1] (main.js:131)             */
+  double star_threshold;       /* RTB_SAMPLER_STARS: 0.001 (main.js:137)                         */
+  double star_gain;            /* RTB_SAMPLER_STARS: 1000  (main.js:138)                         */
+} RtbMaterial;
+
+/* createSphere(o, r, m) main.js:408-418.  The reference stores r*r, never r (main.js:412-413).
+ * surface_area is only used by the host-side sort (main.js:159-163) and is not part of the ABI:
+ * spheres arrive ALREADY in post-sort order — array order fixes closest-hit ties (main.js:229),
+ * the self-shadow skip index (main.js:294) and the occluder loop order (main.js:293-304). */
+typedef struct RtbSphere {
+  double origin[3];
+  double r2;
+  RtbMaterial mtl;
+} RtbSphere;
+
+/* createTexture() main.js:339-341: {width,height,texels}.  texels = RGBA8, row-major, w*h*4 bytes
+ * (what getImageData returns at main.js:388-391, or checkerTexture writes at main.js:353-373). */
+typedef struct RtbTexture {
+  int32_t width;
+  int32_t height;
+  const uint8_t* texels;
+} RtbTexture;
+
+typedef struct RtbSceneDesc {
+  uint32_t abi_version;                 /* RTB_ABI_VERSION                                       */
+  int32_t n_spheres;
+  const RtbSphere* spheres;             /* post-sort order                                       */
+  int32_t n_textures;
+  const RtbTexture* textures;
+  int32_t n_lights;                     /* 2 in the reference (main.js:283)                      */
+  double lights[RTB_MAX_LIGHTS][3];     /* [[5,10,5],[5,10,0]]                                   */
+  double light_intensity;               /* 50, declared once OUTSIDE the light loop (main.js:284)*/
+  double eps;                           /* 0.001 (main.js:430-436, 445)                          */
+} RtbSceneDesc;
+
+/* Camera + projection: the closure variables of main() that spanish() reads (main.js:85-105). */
+typedef struct RtbCamera {
+  int32_t width, height;                /* canvas.width / canvas.height (main.js:79-80)          */
+  double origin[3];
+  double axisX[3], axisY[3], axisZ[3];
+  double projW, projH, projD;           /* W/2, H/2, projW / tan(30 deg) (main.js:103-105)       */
+  int32_t camera_mode;                  /* RTB_CAMERA_*                                          */
+  int32_t _pad;
+} RtbCamera;
+
+typedef struct RtbRenderOpts {
+  int32_t segs;          /* recursion budget passed to intersectWorld; 8 at main.js:194          */
+  int32_t spp_grid;      /* g: g*g regular stratified sub-samples per pixel; 1 = reference, 4 = 16 spp */
+  int32_t precision;     /* RTB_PRECISION_*                                                      */
+  int32_t kernel;        /* RTB_KERNEL_*                                                         */
+  int32_t star_mode;     /* RTB_STARS_*                                                          */
+  int32_t y0, y1;        /* row range [y0,y1) to render; y1 <= 0 means height.  Rows outside are
+                            left untouched (the reference hands back row by row, main.js:200)    */
+  int32_t stripe_rows;   /* multi-GPU interleaving: rows are grouped in stripes of stripe_rows;   */
+  int32_t stripe_rank;   /* this call renders stripes with (stripe_index % stripe_world) ==       */
+  int32_t stripe_world;  /* stripe_rank.  stripe_world <= 1 disables striping.                    */
+  uint64_t star_seed;    /* RTB_STARS_HASH seed                                                   */
+} RtbRenderOpts;
+
+/* Filled by every render call when non-NULL.  Device-side counts, not the oracle's. */
+typedef struct RtbStats {
+  double kernel_ms;          /* CUDA-event time of all kernels of the call                       */
+  double h2d_ms, d2h_ms;     /* copies inside the call (0 for the device entry point)            */
+  uint64_t nodes;            /* intersectWorld invocations with segs > 0 (tree nodes)            */
+  uint64_t shadow_rays;      /* light iterations that passed shadow_dot > 0 (main.js:292)        */
+  uint64_t sphere_tests;     /* ray-sphere tests the DEVICE executed (<= reference's count)      */
+  uint32_t launches;         /* kernel launches issued                                           */
+  uint32_t bands;            /* row bands the frame was split into (wavefront queues)            */
+} RtbStats;
+
+typedef struct RtbScene_* rtb_scene_t;
+
+/* ---- entry points ---------------------------------------------------------------------------- */
+
+/* Select the CUDA device (a negative value picks the current device) and create library streams.
+ * Fails with RTB_ERR_NO_DEVICE when no device exists. Idempotent per process. */
+int rtb_init(int device);
+void rtb_shutdown(void);
+
+/* Validate and upload a scene (spheres, materials, textures, lights).  Immutable afterwards.
+ * Replaces: the `objects` array + `texture_unit*` closures of main() (main.js:107-163). */
+int rtb_scene_create(const RtbSceneDesc* desc, rtb_scene_t* out);
+void rtb_scene_destroy(rtb_scene_t scene);
+
+/* Render one frame into a caller-owned HOST buffer of width*height*4 bytes (RGBA8, row-major,
+ * A = 255): exactly the bytes `colorbuf.data` holds after the last `spanish` tick.
+ * Replaces: redraw()/spanish() pixel loops, main.js:180-199.  H2D of the camera and D2H of the
+ * framebuffer happen inside the call. */
+int rtb_render(rtb_scene_t scene, const RtbCamera* cam, const RtbRenderOpts* opts,
+               uint8_t* out_rgba8, RtbStats* stats_or_null);
+
+/* Same, but `d_out_rgba8` is a DEVICE pointer on the library's device and `cuda_stream` is a
+ * cudaStream_t (as void*, NULL = library stream).  Asynchronous w.r.t. the host unless stats are
+ * requested.  Used by the multi-GPU host layer, which all-gathers stripes with NCCL. */
+int rtb_render_device(rtb_scene_t scene, const RtbCamera* cam, const RtbRenderOpts* opts,
+                      void* d_out_rgba8, void* cuda_stream, RtbStats* stats_or_null);
+
+/* Frame batch (config C5: orbit animation): nframes cameras, nframes*W*H*4 bytes out (host). */
+int rtb_render_batch(rtb_scene_t scene, const RtbCamera* cams, int32_t nframes,
+                     const RtbRenderOpts* opts, uint8_t* out_rgba8, RtbStats* stats_or_null);
+
+/* De-interleave an all-gathered stripe buffer ([rank][local stripe rows][W*4]) into a row-major
+ * framebuffer; both device pointers.  Used after ncclAllGather in the multi-GPU path. */
+int rtb_unstripe_device(const void* d_gathered, void* d_frame, int32_t width, int32_t height,
+                        int32_t stripe_rows, int32_t stripe_world, void* cuda_stream);
+
+/* Number of rows rank `stripe_rank` owns / the padded per-rank row count used by the gather. */
+int32_t rtb_stripe_local_rows(int32_t height, int32_t stripe_rows, int32_t stripe_rank,
+                              int32_t stripe_world);
+int32_t rtb_stripe_padded_rows(int32_t height, int32_t stripe_rows, int32_t stripe_world);
+
+/* Reference defaults (the literals of main.js) for the option/scene scalars. */
+void rtb_default_opts(RtbRenderOpts* opts);
+
+const char* rtb_last_error(void);
+const char* rtb_version(void);          /* "rtb200 <abi> sm_100a" */
+uint32_t rtb_abi_version(void);
+/* Device properties the bench needs without importing anything else: SM count, clock (kHz). */
+int rtb_device_info(int32_t* sm_count, int32_t* clock_khz, char* name_buf, int32_t name_len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTB200_H */
