@@ -7,6 +7,9 @@ The directory name carries hyphens (it is the name the build contract fixes), so
 Layout: csrc/ (CUDA kernels + C ABI, built to csrc/librtb200.so), scene.py (mirror of main.js's
 constructors), scenes.py (BASELINE.json workloads), render.py (Renderer: the redraw() replacement),
 multigpu.py (row-stripe / frame-batch sharding over torch.distributed + NCCL).
+
+Importing the package never touches CUDA; constructing a Renderer does, and raises if the CUDA
+library is not built or no GPU is visible (there is no CPU render path).
 """
 from . import _abi
 from ._abi import (RTB_CAMERA_BASIS, RTB_CAMERA_REFERENCE, RTB_KERNEL_AUTO, RTB_KERNEL_PIXEL,
@@ -16,17 +19,4 @@ from .scene import (Camera, Material, SceneDesc, Sphere, Texture, checkerSampler
                     colorSampler, createMaterial, createSphere, createTexture, loadTexture, make_opts,
                     sortObjects, starSampler, textureFromRGBA, textureSampler)
 from . import scenes
-
-__all__ = [n for n in dir() if not n.startswith("__")]
-
-
-def __getattr__(name):
-    # Renderer and the multi-GPU layer need the CUDA library / torch; import them lazily so that
-    # scene construction (and the CPU test-suite) works on a box without a GPU.
-    if name in ("Renderer", "render"):
-        from . import render as _r
-        return getattr(_r, name) if name == "Renderer" else _r
-    if name == "multigpu":
-        from . import multigpu as _m
-        return _m
-    raise AttributeError(name)
+from .render import Renderer, device_info

@@ -91,6 +91,7 @@ class RtbRenderOpts(C.Structure):
         ("stripe_rows", C.c_int32),
         ("stripe_rank", C.c_int32),
         ("stripe_world", C.c_int32),
+        ("out_packed", C.c_int32),
         ("star_seed", C.c_uint64),
     ]
 

@@ -1,0 +1,555 @@
+// abi.cu — implementation of include/rtb200.h: device setup, scene upload, the render entry points
+// (host buffer, device buffer, frame batch), stripe bookkeeping for the multi-GPU layer, errors.
+// No CPU fallback anywhere: without a CUDA device every computing entry point fails.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include "rtb_internal.h"
+
+RtbGlobal g_rtb;
+static thread_local char t_err[512] = "";
+
+void rtb_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(t_err, sizeof t_err, fmt, ap);
+  va_end(ap);
+}
+
+namespace {
+
+template <typename T>
+void fill_material(DevMaterial<T>& d, const RtbMaterial& m) {
+  for (int i = 0; i < 3; i++) d.color[i] = (T)m.color[i];
+  for (int i = 0; i < 5; i++) d.albedo[i] = (T)m.albedo[i];
+  d.specular_exponent = (T)m.specular_exponent;
+  d.refract_index = (T)m.refract_index;
+  d.checker_freq[0] = (T)m.checker_freq[0];
+  d.checker_freq[1] = (T)m.checker_freq[1];
+  for (int c = 0; c < 2; c++)
+    for (int i = 0; i < 3; i++) d.checker_color[c][i] = (T)m.checker_color[c][i];
+  d.star_threshold = (T)m.star_threshold;
+  d.star_gain = (T)m.star_gain;
+  d.sampler_kind = m.sampler_kind;
+  d.texture_unit = m.texture_unit;
+}
+
+template <typename T>
+void fill_scene_view(DevSceneT<T>& v, const RtbScene_* s, const RtbSceneDesc* d, const T* geom,
+                     const DevMaterial<T>* mtl) {
+  v.n_spheres = s->n_spheres;
+  v.n_textures = s->n_textures;
+  v.n_lights = s->n_lights;
+  v._pad = 0;
+  v.geom = geom;
+  v.mtl = mtl;
+  v.tex = s->d_tex;
+  v.texels = s->d_texels;
+  for (int k = 0; k < RTB_MAX_LIGHTS; k++)
+    for (int c = 0; c < 3; c++) v.lights[k][c] = k < s->n_lights ? (T)d->lights[k][c] : (T)0;
+  v.light_intensity = (T)d->light_intensity;
+  v.eps = (T)d->eps;
+}
+
+int validate_scene(const RtbSceneDesc* d) {
+  if (!d) { rtb_set_error("scene description is NULL"); return RTB_ERR_INVALID; }
+  if (d->abi_version != RTB_ABI_VERSION) {
+    rtb_set_error("abi_version %u, library speaks %u", d->abi_version, RTB_ABI_VERSION);
+    return RTB_ERR_INVALID;
+  }
+  if (d->n_spheres < 0 || d->n_spheres > (1 << 20)) { rtb_set_error("n_spheres out of range"); return RTB_ERR_INVALID; }
+  if (d->n_spheres > 0 && !d->spheres) { rtb_set_error("spheres is NULL"); return RTB_ERR_INVALID; }
+  if (d->n_textures < 0 || d->n_textures > 4096) { rtb_set_error("n_textures out of range"); return RTB_ERR_INVALID; }
+  if (d->n_textures > 0 && !d->textures) { rtb_set_error("textures is NULL"); return RTB_ERR_INVALID; }
+  if (d->n_lights < 0 || d->n_lights > RTB_MAX_LIGHTS) {
+    rtb_set_error("n_lights must be 0..%d", RTB_MAX_LIGHTS);
+    return RTB_ERR_INVALID;
+  }
+  if (!(d->eps == d->eps) || !(d->light_intensity == d->light_intensity)) {
+    rtb_set_error("eps / light_intensity is NaN");
+    return RTB_ERR_INVALID;
+  }
+  for (int t = 0; t < d->n_textures; t++) {
+    const RtbTexture& tx = d->textures[t];
+    if (tx.width <= 0 || tx.height <= 0 || tx.width > 32768 || tx.height > 32768 || !tx.texels) {
+      rtb_set_error("texture %d: bad size %dx%d or NULL texels", t, tx.width, tx.height);
+      return RTB_ERR_INVALID;
+    }
+  }
+  for (int i = 0; i < d->n_spheres; i++) {
+    const RtbMaterial& m = d->spheres[i].mtl;
+    if (m.sampler_kind < RTB_SAMPLER_COLOR || m.sampler_kind > RTB_SAMPLER_STARS) {
+      rtb_set_error("sphere %d: unknown sampler_kind %d", i, m.sampler_kind);
+      return RTB_ERR_INVALID;
+    }
+    if (m.sampler_kind == RTB_SAMPLER_TEXTURE && (m.texture_unit < 0 || m.texture_unit >= d->n_textures)) {
+      rtb_set_error("sphere %d: texture_unit %d outside 0..%d", i, m.texture_unit, d->n_textures - 1);
+      return RTB_ERR_INVALID;
+    }
+  }
+  return RTB_OK;
+}
+
+int validate_render(const RtbScene_* s, const RtbCamera* cam, const RtbRenderOpts* o, const void* out) {
+  if (!g_rtb.inited) { rtb_set_error("rtb_init() has not been called"); return RTB_ERR_NOT_INIT; }
+  if (!s || !cam || !o || !out) { rtb_set_error("NULL argument"); return RTB_ERR_INVALID; }
+  if (cam->width <= 0 || cam->height <= 0 || (long long)cam->width * cam->height > (1ll << 31)) {
+    rtb_set_error("bad canvas size %dx%d", cam->width, cam->height);
+    return RTB_ERR_INVALID;
+  }
+  if (o->segs < 0 || o->segs > RTB_MAX_SEGS) { rtb_set_error("segs must be 0..%d", RTB_MAX_SEGS); return RTB_ERR_INVALID; }
+  if (o->spp_grid < 1 || o->spp_grid > 16) { rtb_set_error("spp_grid must be 1..16"); return RTB_ERR_INVALID; }
+  if (o->precision != RTB_PRECISION_FP32 && o->precision != RTB_PRECISION_FP64) {
+    rtb_set_error("unknown precision %d", o->precision);
+    return RTB_ERR_INVALID;
+  }
+  if (o->kernel < RTB_KERNEL_AUTO || o->kernel > RTB_KERNEL_WAVEFRONT) {
+    rtb_set_error("unknown kernel %d", o->kernel);
+    return RTB_ERR_INVALID;
+  }
+  if (o->kernel == RTB_KERNEL_WAVEFRONT && o->precision == RTB_PRECISION_FP64) {
+    rtb_set_error("the wavefront pipeline is fp32 only");
+    return RTB_ERR_UNSUPPORTED;
+  }
+  if (o->star_mode != RTB_STARS_OFF && o->star_mode != RTB_STARS_HASH) {
+    rtb_set_error("unknown star_mode %d", o->star_mode);
+    return RTB_ERR_INVALID;
+  }
+  if (cam->camera_mode != RTB_CAMERA_REFERENCE && cam->camera_mode != RTB_CAMERA_BASIS) {
+    rtb_set_error("unknown camera_mode %d", cam->camera_mode);
+    return RTB_ERR_INVALID;
+  }
+  if (o->y0 < 0 || o->y0 > cam->height || o->y1 > cam->height || (o->y1 > 0 && o->y1 < o->y0)) {
+    rtb_set_error("bad row range [%d,%d) for height %d", o->y0, o->y1, cam->height);
+    return RTB_ERR_INVALID;
+  }
+  if (o->stripe_world > 1 && (o->stripe_rows <= 0 || o->stripe_rank < 0 || o->stripe_rank >= o->stripe_world)) {
+    rtb_set_error("bad stripe spec rows=%d rank=%d world=%d", o->stripe_rows, o->stripe_rank, o->stripe_world);
+    return RTB_ERR_INVALID;
+  }
+  return RTB_OK;
+}
+
+RowMap make_rowmap(const RtbCamera* cam, const RtbRenderOpts* o) {
+  RowMap rm;
+  rm.y0 = o->y0;
+  rm.y1 = o->y1 <= 0 ? cam->height : o->y1;
+  rm.S = o->stripe_rows;
+  rm.rank = o->stripe_rank;
+  rm.world = o->stripe_world;
+  rm.packed = o->out_packed;
+  rm.width = cam->width;
+  return rm;
+}
+
+template <typename T>
+DevFrameT<T> make_frame(const RtbCamera* cam, const RtbRenderOpts* o) {
+  DevFrameT<T> f;
+  memset(&f, 0, sizeof f);
+  f.width = cam->width; f.height = cam->height;
+  f.segs = o->segs; f.spp_grid = o->spp_grid;
+  f.star_mode = o->star_mode; f.camera_mode = cam->camera_mode;
+  f.y0 = o->y0; f.y1 = o->y1 <= 0 ? cam->height : o->y1;
+  f.stripe_rows = o->stripe_rows; f.stripe_rank = o->stripe_rank; f.stripe_world = o->stripe_world;
+  f.out_packed = o->out_packed;
+  f.star_seed = o->star_seed;
+  for (int c = 0; c < 3; c++) {
+    f.origin[c] = (T)cam->origin[c]; f.axisX[c] = (T)cam->axisX[c];
+    f.axisY[c] = (T)cam->axisY[c]; f.axisZ[c] = (T)cam->axisZ[c];
+  }
+  f.projW = (T)cam->projW; f.projH = (T)cam->projH; f.projD = (T)cam->projD;
+  return f;
+}
+
+// Launch the kernels of one frame into d_out on stream st.  Synchronises only on the wavefront path
+// (queue-overflow check) or when counters are wanted.
+int render_to_device(RtbScene_* s, const RtbCamera* cam, const RtbRenderOpts* o, uint8_t* d_out,
+                     cudaStream_t st, RtbStats* stats) {
+  const RowMap rm = make_rowmap(cam, o);
+  int kernel = o->kernel;
+  if (kernel == RTB_KERNEL_AUTO)
+    kernel = (o->precision == RTB_PRECISION_FP64 || s->n_spheres == 0) ? RTB_KERNEL_PIXEL : RTB_KERNEL_WAVEFRONT;
+  uint32_t launches = 0;
+  if (kernel == RTB_KERNEL_WAVEFRONT) {
+    const DevFrameT<float> fr = make_frame<float>(cam, o);
+    return wf_render(s, cam, fr, rm, d_out, st, stats, stats != nullptr);
+  }
+  unsigned long long* ctr = stats ? s->d_counters : nullptr;
+  if (ctr) RTB_CUDA(cudaMemsetAsync(ctr, 0, 3 * sizeof(unsigned long long), st));
+  int rc;
+  if (o->precision == RTB_PRECISION_FP64) {
+    const DevFrameT<double> fr = make_frame<double>(cam, o);
+    rc = launch_pixel_f64(s->sc64, fr, rm, d_out, ctr, st, &launches);
+  } else {
+    const DevFrameT<float> fr = make_frame<float>(cam, o);
+    rc = launch_pixel_f32(s->sc32, fr, rm, d_out, ctr, st, &launches);
+  }
+  if (rc != RTB_OK) return rc;
+  if (stats) {
+    unsigned long long h[3];
+    RTB_CUDA(cudaMemcpyAsync(h, ctr, sizeof h, cudaMemcpyDeviceToHost, st));
+    RTB_CUDA(cudaStreamSynchronize(st));
+    stats->nodes += h[0]; stats->shadow_rays += h[1]; stats->sphere_tests += h[2];
+    stats->launches += launches;
+    stats->bands += 1;
+  }
+  return RTB_OK;
+}
+
+int ensure_frame(RtbScene_* s, int slot, size_t bytes) {
+  if (s->frame_cap[slot] >= bytes) return RTB_OK;
+  if (s->d_frame[slot]) cudaFree(s->d_frame[slot]);
+  s->d_frame[slot] = nullptr; s->frame_cap[slot] = 0;
+  RTB_CUDA(cudaMalloc(&s->d_frame[slot], bytes));
+  s->frame_cap[slot] = bytes;
+  return RTB_OK;
+}
+
+// D2H of the rows this call rendered.  Packed: one contiguous copy.  Natural layout: the rows sit at
+// their frame position; stripes become one strided 2-D copy (+ a ragged tail).
+int copy_rows_to_host(const RowMap& rm, const uint8_t* d_frame, uint8_t* h_out, int height, cudaStream_t st) {
+  const size_t row_bytes = (size_t)rm.width * 4;
+  const int n_local = rm.n_local();
+  if (n_local <= 0) return RTB_OK;
+  if (rm.packed) {
+    RTB_CUDA(cudaMemcpyAsync(h_out, d_frame, row_bytes * n_local, cudaMemcpyDeviceToHost, st));
+    return RTB_OK;
+  }
+  if (rm.world <= 1 || rm.S <= 0) {
+    RTB_CUDA(cudaMemcpyAsync(h_out + row_bytes * rm.y0, d_frame + row_bytes * rm.y0,
+                             row_bytes * (size_t)(rm.y1 - rm.y0), cudaMemcpyDeviceToHost, st));
+    return RTB_OK;
+  }
+  (void)height;
+  // runs of consecutive owned rows
+  int l = 0;
+  while (l < n_local) {
+    const int y = rm.local_to_y(l);
+    int run = 1;
+    while (l + run < n_local && rm.local_to_y(l + run) == y + run) run++;
+    // try to batch equally long, equally spaced runs into one 2-D copy
+    int reps = 1;
+    const int pitch_rows = rm.S * rm.world;
+    while (l + (reps + 1) * run <= n_local && rm.local_to_y(l + reps * run) == y + reps * pitch_rows) {
+      bool same = true;
+      for (int i = 1; i < run && same; i++) same = rm.local_to_y(l + reps * run + i) == y + reps * pitch_rows + i;
+      if (!same) break;
+      reps++;
+    }
+    if (reps > 1) {
+      RTB_CUDA(cudaMemcpy2DAsync(h_out + row_bytes * y, row_bytes * pitch_rows, d_frame + row_bytes * y,
+                                 row_bytes * pitch_rows, row_bytes * run, reps, cudaMemcpyDeviceToHost, st));
+    } else {
+      RTB_CUDA(cudaMemcpyAsync(h_out + row_bytes * y, d_frame + row_bytes * y, row_bytes * run,
+                               cudaMemcpyDeviceToHost, st));
+    }
+    l += run * reps;
+  }
+  return RTB_OK;
+}
+
+__global__ void unstripe_kernel(const uint32_t* __restrict__ gathered, uint32_t* __restrict__ frame, int W,
+                                int H, int S, int world, int padded_rows) {
+  // gathered: [rank][padded_rows][W]; local row l of rank r is frame row (l / S) * S * world + r * S + l % S
+  const long long total = (long long)H * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int y = (int)(i / W), x = (int)(i % W);
+    const int stripe = y / S, r = stripe % world, l = (stripe / world) * S + y % S;
+    frame[i] = gathered[((size_t)r * padded_rows + l) * W + x];
+  }
+}
+
+}  // namespace
+
+// ---- C ABI ------------------------------------------------------------------------------------------------
+// The library is built with -fvisibility=hidden; only the entry points of include/rtb200.h are exported.
+#pragma GCC visibility push(default)
+extern "C" {
+
+int rtb_init(int device) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0) {
+    rtb_set_error("no CUDA device visible (%s); this library has no CPU fallback",
+                  e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    (void)cudaGetLastError();
+    return RTB_ERR_NO_DEVICE;
+  }
+  if (device < 0) {
+    if (g_rtb.inited) return RTB_OK;
+    RTB_CUDA(cudaGetDevice(&device));
+  }
+  if (device >= count) { rtb_set_error("device %d of %d", device, count); return RTB_ERR_INVALID; }
+  if (g_rtb.inited && g_rtb.device == device) { RTB_CUDA(cudaSetDevice(device)); return RTB_OK; }
+  if (g_rtb.inited) rtb_shutdown();
+  RTB_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  RTB_CUDA(cudaGetDeviceProperties(&prop, device));
+  g_rtb.device = device;
+  g_rtb.sm_count = prop.multiProcessorCount;
+  int khz = 0;
+  cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
+  g_rtb.clock_khz = khz;
+  g_rtb.smem_optin = prop.sharedMemPerBlockOptin;
+  snprintf(g_rtb.name, sizeof g_rtb.name, "%s", prop.name);
+  RTB_CUDA(cudaStreamCreateWithFlags(&g_rtb.stream, cudaStreamNonBlocking));
+  RTB_CUDA(cudaStreamCreateWithFlags(&g_rtb.copy_stream, cudaStreamNonBlocking));
+  RTB_CUDA(cudaEventCreate(&g_rtb.ev0));
+  RTB_CUDA(cudaEventCreate(&g_rtb.ev1));
+  RTB_CUDA(cudaEventCreate(&g_rtb.ev2));
+  RTB_CUDA(cudaEventCreate(&g_rtb.ev3));
+  for (int i = 0; i < 2; i++) {
+    RTB_CUDA(cudaEventCreateWithFlags(&g_rtb.frame_done[i], cudaEventDisableTiming));
+    RTB_CUDA(cudaEventCreateWithFlags(&g_rtb.copy_done[i], cudaEventDisableTiming));
+  }
+  g_rtb.inited = true;
+  return RTB_OK;
+}
+
+void rtb_shutdown(void) {
+  if (!g_rtb.inited) return;
+  cudaDeviceSynchronize();
+  cudaStreamDestroy(g_rtb.stream);
+  cudaStreamDestroy(g_rtb.copy_stream);
+  cudaEventDestroy(g_rtb.ev0); cudaEventDestroy(g_rtb.ev1);
+  cudaEventDestroy(g_rtb.ev2); cudaEventDestroy(g_rtb.ev3);
+  for (int i = 0; i < 2; i++) { cudaEventDestroy(g_rtb.frame_done[i]); cudaEventDestroy(g_rtb.copy_done[i]); }
+  g_rtb = RtbGlobal{};
+}
+
+int rtb_scene_create(const RtbSceneDesc* d, rtb_scene_t* out) {
+  if (!out) { rtb_set_error("out is NULL"); return RTB_ERR_INVALID; }
+  *out = nullptr;
+  if (!g_rtb.inited) { rtb_set_error("rtb_init() has not been called"); return RTB_ERR_NOT_INIT; }
+  int rc = validate_scene(d);
+  if (rc != RTB_OK) return rc;
+  RtbScene_* s = new (std::nothrow) RtbScene_();
+  if (!s) { rtb_set_error("host allocation failed"); return RTB_ERR_OOM; }
+  struct Guard { RtbScene_* s; ~Guard() { if (s) rtb_scene_destroy(s); } } guard{s};
+  const int n = d->n_spheres;
+  s->n_spheres = n; s->n_textures = d->n_textures; s->n_lights = d->n_lights;
+  s->spheres.assign(d->spheres, d->spheres + n);
+  memcpy(s->lights, d->lights, sizeof s->lights);
+  const int na = n > 0 ? n : 1;
+
+  std::vector<double> g64((size_t)na * 4);
+  std::vector<float> g32((size_t)na * 4);
+  std::vector<DevMaterial<double>> m64(na);
+  std::vector<DevMaterial<float>> m32(na);
+  for (int i = 0; i < n; i++) {
+    const RtbSphere& sp = d->spheres[i];
+    for (int c = 0; c < 3; c++) { g64[4 * i + c] = sp.origin[c]; g32[4 * i + c] = (float)sp.origin[c]; }
+    g64[4 * i + 3] = sp.r2; g32[4 * i + 3] = (float)sp.r2;
+    fill_material(m64[i], sp.mtl);
+    fill_material(m32[i], sp.mtl);
+  }
+  RTB_CUDA(cudaMalloc(&s->d_geom64, g64.size() * sizeof(double)));
+  RTB_CUDA(cudaMalloc(&s->d_geom32, g32.size() * sizeof(float)));
+  RTB_CUDA(cudaMalloc(&s->d_mtl64, m64.size() * sizeof(DevMaterial<double>)));
+  RTB_CUDA(cudaMalloc(&s->d_mtl32, m32.size() * sizeof(DevMaterial<float>)));
+  RTB_CUDA(cudaMemcpy(s->d_geom64, g64.data(), g64.size() * sizeof(double), cudaMemcpyHostToDevice));
+  RTB_CUDA(cudaMemcpy(s->d_geom32, g32.data(), g32.size() * sizeof(float), cudaMemcpyHostToDevice));
+  RTB_CUDA(cudaMemcpy(s->d_mtl64, m64.data(), m64.size() * sizeof(DevMaterial<double>), cudaMemcpyHostToDevice));
+  RTB_CUDA(cudaMemcpy(s->d_mtl32, m32.data(), m32.size() * sizeof(DevMaterial<float>), cudaMemcpyHostToDevice));
+
+  // textures: one uchar4 pool, byte-exact copies of the caller's RGBA8 texels
+  std::vector<DevTexture> tex(d->n_textures > 0 ? d->n_textures : 1);
+  size_t pool = 0;
+  for (int t = 0; t < d->n_textures; t++) {
+    tex[t].width = d->textures[t].width; tex[t].height = d->textures[t].height;
+    tex[t].offset = (uint32_t)pool; tex[t]._pad = 0;
+    pool += (size_t)tex[t].width * tex[t].height;
+  }
+  if (pool > 0xffffffffull) { rtb_set_error("texture pool too large"); return RTB_ERR_INVALID; }
+  RTB_CUDA(cudaMalloc(&s->d_tex, tex.size() * sizeof(DevTexture)));
+  RTB_CUDA(cudaMemcpy(s->d_tex, tex.data(), tex.size() * sizeof(DevTexture), cudaMemcpyHostToDevice));
+  RTB_CUDA(cudaMalloc(&s->d_texels, (pool > 0 ? pool : 1) * sizeof(uchar4)));
+  for (int t = 0; t < d->n_textures; t++)
+    RTB_CUDA(cudaMemcpy(s->d_texels + tex[t].offset, d->textures[t].texels,
+                        (size_t)tex[t].width * tex[t].height * 4, cudaMemcpyHostToDevice));
+
+  fill_scene_view<double>(s->sc64, s, d, s->d_geom64, s->d_mtl64);
+  fill_scene_view<float>(s->sc32, s, d, s->d_geom32, s->d_mtl32);
+
+  // wavefront per-light tables (fp64 arithmetic, one rounding to fp32)
+  std::vector<float4> tab(na);
+  for (int k = 0; k < d->n_lights; k++) {
+    for (int i = 0; i < n; i++) {
+      const RtbSphere& sp = d->spheres[i];
+      const double L0 = sp.origin[0] - d->lights[k][0], L1 = sp.origin[1] - d->lights[k][1],
+                   L2 = sp.origin[2] - d->lights[k][2];
+      tab[i] = make_float4((float)L0, (float)L1, (float)L2, (float)((L0 * L0 + L1 * L1 + L2 * L2) - sp.r2));
+    }
+    RTB_CUDA(cudaMalloc(&s->d_light_tab[k], (size_t)na * sizeof(float4)));
+    RTB_CUDA(cudaMemcpy(s->d_light_tab[k], tab.data(), (size_t)na * sizeof(float4), cudaMemcpyHostToDevice));
+  }
+  RTB_CUDA(cudaMalloc(&s->d_primary_tab, (size_t)na * sizeof(float4)));
+  RTB_CUDA(cudaMallocHost(&s->h_primary_tab, (size_t)na * sizeof(float4)));
+  RTB_CUDA(cudaMalloc(&s->d_counters, 3 * sizeof(unsigned long long)));
+  guard.s = nullptr;
+  *out = s;
+  return RTB_OK;
+}
+
+void rtb_scene_destroy(rtb_scene_t s) {
+  if (!s) return;
+  if (g_rtb.inited) cudaDeviceSynchronize();
+  cudaFree(s->d_geom64); cudaFree(s->d_geom32); cudaFree(s->d_mtl64); cudaFree(s->d_mtl32);
+  cudaFree(s->d_tex); cudaFree(s->d_texels);
+  for (int k = 0; k < RTB_MAX_LIGHTS; k++) cudaFree(s->d_light_tab[k]);
+  cudaFree(s->d_primary_tab);
+  if (s->h_primary_tab) cudaFreeHost(s->h_primary_tab);
+  cudaFree(s->d_frame[0]); cudaFree(s->d_frame[1]);
+  cudaFree(s->d_counters);
+  wf_free(s);
+  (void)cudaGetLastError();
+  delete s;
+}
+
+int rtb_render_device(rtb_scene_t s, const RtbCamera* cam, const RtbRenderOpts* o, void* d_out,
+                      void* cuda_stream, RtbStats* stats) {
+  int rc = validate_render(s, cam, o, d_out);
+  if (rc != RTB_OK) return rc;
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : g_rtb.stream;
+  if (stats) { memset(stats, 0, sizeof *stats); RTB_CUDA(cudaEventRecord(g_rtb.ev0, st)); }
+  rc = render_to_device(s, cam, o, (uint8_t*)d_out, st, stats);
+  if (rc != RTB_OK) return rc;
+  if (stats) {
+    RTB_CUDA(cudaEventRecord(g_rtb.ev1, st));
+    RTB_CUDA(cudaEventSynchronize(g_rtb.ev1));
+    float ms = 0;
+    RTB_CUDA(cudaEventElapsedTime(&ms, g_rtb.ev0, g_rtb.ev1));
+    stats->kernel_ms = ms;
+  }
+  return RTB_OK;
+}
+
+int rtb_render(rtb_scene_t s, const RtbCamera* cam, const RtbRenderOpts* o, uint8_t* out, RtbStats* stats) {
+  int rc = validate_render(s, cam, o, out);
+  if (rc != RTB_OK) return rc;
+  const size_t bytes = (size_t)cam->width * cam->height * 4;
+  rc = ensure_frame(s, 0, bytes);
+  if (rc != RTB_OK) return rc;
+  cudaStream_t st = g_rtb.stream;
+  if (stats) memset(stats, 0, sizeof *stats);
+  RTB_CUDA(cudaEventRecord(g_rtb.ev0, st));
+  rc = render_to_device(s, cam, o, s->d_frame[0], st, stats);
+  if (rc != RTB_OK) return rc;
+  RTB_CUDA(cudaEventRecord(g_rtb.ev1, st));
+  const RowMap rm = make_rowmap(cam, o);
+  rc = copy_rows_to_host(rm, s->d_frame[0], out, cam->height, st);
+  if (rc != RTB_OK) return rc;
+  RTB_CUDA(cudaEventRecord(g_rtb.ev2, st));
+  RTB_CUDA(cudaEventSynchronize(g_rtb.ev2));
+  if (stats) {
+    float ms = 0;
+    RTB_CUDA(cudaEventElapsedTime(&ms, g_rtb.ev0, g_rtb.ev1));
+    stats->kernel_ms = ms;
+    RTB_CUDA(cudaEventElapsedTime(&ms, g_rtb.ev1, g_rtb.ev2));
+    stats->d2h_ms = ms;
+  }
+  return RTB_OK;
+}
+
+int rtb_render_batch(rtb_scene_t s, const RtbCamera* cams, int32_t nframes, const RtbRenderOpts* o,
+                     uint8_t* out, RtbStats* stats) {
+  if (nframes < 0 || (nframes > 0 && !cams)) { rtb_set_error("bad frame batch"); return RTB_ERR_INVALID; }
+  if (stats) memset(stats, 0, sizeof *stats);
+  if (nframes == 0) return RTB_OK;
+  if (!o) { rtb_set_error("NULL argument"); return RTB_ERR_INVALID; }
+  if (o->out_packed || o->stripe_world > 1 || o->y0 != 0 || (o->y1 > 0 && o->y1 != cams[0].height)) {
+    rtb_set_error("rtb_render_batch renders whole frames (no stripes / row ranges)");
+    return RTB_ERR_UNSUPPORTED;
+  }
+  size_t off = 0;
+  RTB_CUDA(cudaEventRecord(g_rtb.ev0, g_rtb.stream));
+  // double-buffered: frame f renders on the compute stream while frame f-1 drains on the copy stream
+  for (int f = 0; f < nframes; f++) {
+    int rc = validate_render(s, &cams[f], o, out);
+    if (rc != RTB_OK) return rc;
+    const int slot = f & 1;
+    const size_t bytes = (size_t)cams[f].width * cams[f].height * 4;
+    rc = ensure_frame(s, slot, bytes);
+    if (rc != RTB_OK) return rc;
+    if (f >= 2) RTB_CUDA(cudaStreamWaitEvent(g_rtb.stream, g_rtb.copy_done[slot], 0));
+    RtbStats one;
+    memset(&one, 0, sizeof one);
+    rc = render_to_device(s, &cams[f], o, s->d_frame[slot], g_rtb.stream, stats ? &one : nullptr);
+    if (rc != RTB_OK) return rc;
+    if (stats) {
+      stats->nodes += one.nodes; stats->shadow_rays += one.shadow_rays; stats->sphere_tests += one.sphere_tests;
+      stats->launches += one.launches; stats->bands += one.bands;
+    }
+    RTB_CUDA(cudaEventRecord(g_rtb.frame_done[slot], g_rtb.stream));
+    RTB_CUDA(cudaStreamWaitEvent(g_rtb.copy_stream, g_rtb.frame_done[slot], 0));
+    RTB_CUDA(cudaMemcpyAsync(out + off, s->d_frame[slot], bytes, cudaMemcpyDeviceToHost, g_rtb.copy_stream));
+    RTB_CUDA(cudaEventRecord(g_rtb.copy_done[slot], g_rtb.copy_stream));
+    off += bytes;
+  }
+  RTB_CUDA(cudaEventRecord(g_rtb.ev1, g_rtb.stream));
+  RTB_CUDA(cudaStreamSynchronize(g_rtb.copy_stream));
+  RTB_CUDA(cudaStreamSynchronize(g_rtb.stream));
+  if (stats) {
+    float ms = 0;
+    RTB_CUDA(cudaEventElapsedTime(&ms, g_rtb.ev0, g_rtb.ev1));
+    stats->kernel_ms = ms;
+  }
+  return RTB_OK;
+}
+
+int32_t rtb_stripe_local_rows(int32_t height, int32_t stripe_rows, int32_t rank, int32_t world) {
+  RowMap rm{0, height, stripe_rows, rank, world, 0, 0};
+  return rm.n_local();
+}
+
+int32_t rtb_stripe_padded_rows(int32_t height, int32_t stripe_rows, int32_t world) {
+  int32_t m = 0;
+  for (int r = 0; r < (world > 1 ? world : 1); r++) {
+    const int32_t v = rtb_stripe_local_rows(height, stripe_rows, r, world);
+    if (v > m) m = v;
+  }
+  return m;
+}
+
+int rtb_unstripe_device(const void* d_gathered, void* d_frame, int32_t width, int32_t height,
+                        int32_t stripe_rows, int32_t stripe_world, void* cuda_stream) {
+  if (!g_rtb.inited) { rtb_set_error("rtb_init() has not been called"); return RTB_ERR_NOT_INIT; }
+  if (!d_gathered || !d_frame || width <= 0 || height <= 0 || stripe_rows <= 0 || stripe_world < 1) {
+    rtb_set_error("bad unstripe arguments");
+    return RTB_ERR_INVALID;
+  }
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : g_rtb.stream;
+  const int padded = rtb_stripe_padded_rows(height, stripe_rows, stripe_world);
+  unstripe_kernel<<<g_rtb.sm_count * 8, 256, 0, st>>>((const uint32_t*)d_gathered, (uint32_t*)d_frame, width,
+                                                     height, stripe_rows, stripe_world, padded);
+  RTB_CUDA(cudaGetLastError());
+  return RTB_OK;
+}
+
+void rtb_default_opts(RtbRenderOpts* o) {
+  if (!o) return;
+  memset(o, 0, sizeof *o);
+  o->segs = 8;                 // main.js:194
+  o->spp_grid = 1;
+  o->precision = RTB_PRECISION_FP32;
+  o->kernel = RTB_KERNEL_AUTO;
+  o->star_mode = RTB_STARS_OFF;
+}
+
+const char* rtb_last_error(void) { return t_err; }
+const char* rtb_version(void) { return "rtb200 abi 1 sm_100a"; }
+uint32_t rtb_abi_version(void) { return RTB_ABI_VERSION; }
+
+int rtb_device_info(int32_t* sm_count, int32_t* clock_khz, char* name_buf, int32_t name_len) {
+  if (!g_rtb.inited) { rtb_set_error("rtb_init() has not been called"); return RTB_ERR_NOT_INIT; }
+  if (sm_count) *sm_count = g_rtb.sm_count;
+  if (clock_khz) *clock_khz = g_rtb.clock_khz;
+  if (name_buf && name_len > 0) snprintf(name_buf, (size_t)name_len, "%s", g_rtb.name);
+  return RTB_OK;
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

@@ -1,0 +1,99 @@
+// rtb_internal.h — library-private state shared by abi.cu, pixel_f32/f64.cu and wavefront.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "rtb_device.cuh"
+
+// ---- wavefront (fp32 throughput path) device buffers --------------------------------------------------
+// Nodes = intersectWorld invocations (main.js:220) of the current row band, numbered level by level:
+// level 1 (primary rays) occupies [0, n_sub); the children created while level L is traced are
+// appended contiguously and form level L+1.  All arrays are SoA over the node index.
+struct WfCounters {          // one small device struct, zeroed per band
+  uint32_t node_count;       // next free node
+  uint32_t blocks_done;      // last-block ticket for level bookkeeping
+  uint32_t overflow;         // set when a child did not fit in cap_nodes
+  uint32_t _pad;
+  uint32_t level_end[RTB_MAX_SEGS + 1];   // level L = [level_end[L-1], level_end[L]); level_end[0] = 0
+  uint32_t sq_count[RTB_MAX_LIGHTS];      // shadow queue fill per light
+  unsigned long long stat_nodes, stat_shadow, stat_tests;
+};
+
+struct WfBuffers {
+  uint32_t cap_nodes;
+  float4* ray_o;   // ox, oy, oz, dx                        (levels >= 2)
+  float4* ray_d;   // dy, dz, weight (albedo[3|4] of parent), unused
+  int2* link;      // parent node, meta = path code | segs_left << 24
+  float4* pos;     // hit.p.xyz, hit_i (int bits); hit_i < 0: no hit (main.js:231)
+  float4* base;    // sampler rgb, facing-light mask (int bits)
+  float4* lq;      // q0, s0, q1, s1   (q = shadow_dot / light_mag, s = pow(spec_dot, se))
+  float4* lq2;     // same for lights 2, 3 (only allocated when n_lights > 2)
+  float4* acc;     // light_intensity carry, diffuse sum, specular sum, unused
+  float4* child_a; // reflect_color (already scaled by albedo[3]) written by the child's compose
+  float4* child_b; // refract_color (scaled by albedo[4])
+  uint32_t* sq[RTB_MAX_LIGHTS];   // shadow queues: node indices waiting for light k's occluder sweep
+  WfCounters* ctr;
+};
+
+struct RtbScene_ {
+  int n_spheres = 0, n_textures = 0, n_lights = 0;
+  std::vector<RtbSphere> spheres;         // host copy (primary table is camera dependent)
+  double lights[RTB_MAX_LIGHTS][3];
+  // device, both precisions
+  double* d_geom64 = nullptr;
+  float* d_geom32 = nullptr;
+  DevMaterial<double>* d_mtl64 = nullptr;
+  DevMaterial<float>* d_mtl32 = nullptr;
+  DevTexture* d_tex = nullptr;
+  uchar4* d_texels = nullptr;
+  DevSceneT<double> sc64;
+  DevSceneT<float> sc32;
+  // wavefront tables: per light (C - light, |C - light|^2 - r2), computed in fp64 once per scene;
+  // the primary table (C - origin, |C - origin|^2 - r2) is rebuilt per camera.
+  float4* d_light_tab[RTB_MAX_LIGHTS] = {nullptr, nullptr, nullptr, nullptr};
+  float4* d_primary_tab = nullptr;
+  float4* h_primary_tab = nullptr;        // pinned staging
+  double primary_origin[3] = {0, 0, 0};
+  bool primary_valid = false;
+  // per-scene output + workspace
+  uint8_t* d_frame[2] = {nullptr, nullptr};
+  size_t frame_cap[2] = {0, 0};
+  WfBuffers wf = {};
+  size_t wf_bytes = 0;
+  unsigned long long* d_counters = nullptr;   // 3 x u64 for the pixel kernels
+};
+
+struct RtbGlobal {
+  bool inited = false;
+  int device = -1;
+  int sm_count = 0;
+  int clock_khz = 0;
+  size_t smem_optin = 0;
+  char name[128] = {0};
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+  cudaEvent_t frame_done[2] = {nullptr, nullptr}, copy_done[2] = {nullptr, nullptr};
+};
+extern RtbGlobal g_rtb;
+
+void rtb_set_error(const char* fmt, ...);
+#define RTB_CUDA(call)                                                                     \
+  do {                                                                                     \
+    cudaError_t e_ = (call);                                                               \
+    if (e_ != cudaSuccess) {                                                               \
+      rtb_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+      return e_ == cudaErrorMemoryAllocation ? RTB_ERR_OOM : RTB_ERR_CUDA;                 \
+    }                                                                                      \
+  } while (0)
+
+// pixel kernels (one TU per precision so that only the fp64 one is built with -fmad=false)
+int launch_pixel_f64(const DevSceneT<double>& sc, const DevFrameT<double>& fr, const RowMap& rm,
+                     uint8_t* d_out, unsigned long long* d_counters, cudaStream_t st, uint32_t* launches);
+int launch_pixel_f32(const DevSceneT<float>& sc, const DevFrameT<float>& fr, const RowMap& rm,
+                     uint8_t* d_out, unsigned long long* d_counters, cudaStream_t st, uint32_t* launches);
+
+// wavefront pipeline: renders the rows of `rm` into d_out, splitting into bands as needed.
+int wf_render(RtbScene_* s, const RtbCamera* cam, const DevFrameT<float>& fr, const RowMap& rm,
+              uint8_t* d_out, cudaStream_t st, RtbStats* stats, bool want_counts);
+void wf_free(RtbScene_* s);

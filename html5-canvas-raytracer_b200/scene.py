@@ -304,10 +304,11 @@ class SceneDesc:
 
 def make_opts(segs=8, spp_grid=1, precision=A.RTB_PRECISION_FP32, kernel=A.RTB_KERNEL_AUTO,
               star_mode=A.RTB_STARS_OFF, y0=0, y1=0, stripe_rows=0, stripe_rank=0, stripe_world=0,
-              star_seed=0) -> A.RtbRenderOpts:
+              star_seed=0, out_packed=0) -> A.RtbRenderOpts:
     o = A.RtbRenderOpts()
     o.segs, o.spp_grid, o.precision, o.kernel, o.star_mode = segs, spp_grid, precision, kernel, star_mode
     o.y0, o.y1 = y0, y1
     o.stripe_rows, o.stripe_rank, o.stripe_world = stripe_rows, stripe_rank, stripe_world
     o.star_seed = star_seed
+    o.out_packed = out_packed
     return o

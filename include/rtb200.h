@@ -140,6 +140,9 @@ typedef struct RtbRenderOpts {
   int32_t stripe_rows;   /* multi-GPU interleaving: rows are grouped in stripes of stripe_rows;   */
   int32_t stripe_rank;   /* this call renders stripes with (stripe_index % stripe_world) ==       */
   int32_t stripe_world;  /* stripe_rank.  stripe_world <= 1 disables striping.                    */
+  int32_t out_packed;    /* 0: rows land at their natural position of a full W*H frame (others
+                            untouched); 1: the rows this call renders are packed contiguously, in
+                            ascending y, from the start of the buffer (the all-gather send layout) */
   uint64_t star_seed;    /* RTB_STARS_HASH seed                                                   */
 } RtbRenderOpts;
 

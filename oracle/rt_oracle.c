@@ -221,12 +221,15 @@ static void sampler(Ctx* cx, const Hit* hit, uint32_t node_id, double rgb[3]) {
 
 /* ---- intersectWorld main.js:220-337 ------------------------------------------------------------ */
 static void intersectWorld(Ctx* cx, int segs, const double org[3], const double dir[3],
-                           double out[3]) {
+                           uint32_t path, double out[3]) {
   const RtbSceneDesc* s = cx->s;
   const int n = s->n_spheres;
   if (segs == 0) { out[0] = out[1] = out[2] = 0; cx->hit_cap = 1; return; } /* main.js:221 */
   cx->c.nodes++;
-  const uint32_t node_id = cx->node_in_px++;   /* pre-order id of this node within the pixel */
+  /* path code of this node inside the pixel: root 1, reflect child 2k, refract child 2k+1 — the
+   * traversal-order-independent key of RTB_STARS_HASH (not part of the reference) */
+  const uint32_t node_id = path;
+  cx->node_in_px++;
 
   int hit_i = -1;                              /* main.js:223-230 */
   Hit hit; hit.t = INFINITY;
@@ -276,12 +279,12 @@ static void intersectWorld(Ctx* cx, int segs, const double org[3], const double 
 
   double reflect_color[3] = {0, 0, 0};         /* main.js:268-272 */
   if (reflect_len != 0) {
-    intersectWorld(cx, segs - 1, hit.p, reflect_dir, reflect_color);
+    intersectWorld(cx, segs - 1, hit.p, reflect_dir, 2u * path, reflect_color);
     scale3D(reflect_color, reflect_color, m->albedo[3]);
   }
   double refract_color[3] = {0, 0, 0};         /* main.js:274-278 */
   if (refract_len != 0) {
-    intersectWorld(cx, segs - 1, hit.p, refract_dir, refract_color);
+    intersectWorld(cx, segs - 1, hit.p, refract_dir, 2u * path + 1u, refract_color);
     scale3D(refract_color, refract_color, m->albedo[4]);
   }
 
@@ -366,7 +369,7 @@ static void render_pixel(Ctx* cx, const RtbCamera* cam, const RtbRenderOpts* o, 
       normal3D(ray, ray);                        /* main.js:193 */
       cx->px = (uint32_t)x; cx->py = (uint32_t)y; cx->sub = (uint32_t)(j * g + i);
       cx->node_in_px = 0; cx->hit_cap = 0;
-      intersectWorld(cx, o->segs, cam->origin, ray, rgb);  /* main.js:194 */
+      intersectWorld(cx, o->segs, cam->origin, ray, 1u, rgb);  /* main.js:194 */
       if (cx->node_in_px > cx->c.max_nodes_px) cx->c.max_nodes_px = cx->node_in_px;
       if (cx->hit_cap) cx->c.depth_cap_px++;
       if (g == 1) { acc[0] = rgb[0]; acc[1] = rgb[1]; acc[2] = rgb[2]; }
@@ -442,7 +445,7 @@ int oracle_trace_ray(const RtbSceneDesc* s, int segs, const double org[3], const
                      double out_rgb[3], OracleCounters* counters_or_null) {
   Ctx cx; memset(&cx, 0, sizeof cx);
   cx.s = s;
-  intersectWorld(&cx, segs, org, dir, out_rgb);
+  intersectWorld(&cx, segs, org, dir, 1u, out_rgb);
   if (counters_or_null) *counters_or_null = cx.c;
   return 0;
 }
