@@ -106,6 +106,10 @@ class RtbStats(C.Structure):
         ("sphere_tests", C.c_uint64),
         ("launches", C.c_uint32),
         ("bands", C.c_uint32),
+        ("ms_trace_primary", C.c_double),
+        ("ms_trace_secondary", C.c_double),
+        ("ms_shadow", C.c_double),
+        ("ms_compose", C.c_double),
     ]
 
 

@@ -176,7 +176,7 @@ int render_to_device(RtbScene_* s, const RtbCamera* cam, const RtbRenderOpts* o,
     const DevFrameT<float> fr = make_frame<float>(cam, o);
     return wf_render(s, cam, fr, rm, d_out, st, stats, stats != nullptr);
   }
-  unsigned long long* ctr = stats ? s->d_counters : nullptr;
+  unsigned long long* ctr = stats ? g_rtb.d_counters : nullptr;
   if (ctr) RTB_CUDA(cudaMemsetAsync(ctr, 0, 3 * sizeof(unsigned long long), st));
   int rc;
   if (o->precision == RTB_PRECISION_FP64) {
@@ -198,12 +198,12 @@ int render_to_device(RtbScene_* s, const RtbCamera* cam, const RtbRenderOpts* o,
   return RTB_OK;
 }
 
-int ensure_frame(RtbScene_* s, int slot, size_t bytes) {
-  if (s->frame_cap[slot] >= bytes) return RTB_OK;
-  if (s->d_frame[slot]) cudaFree(s->d_frame[slot]);
-  s->d_frame[slot] = nullptr; s->frame_cap[slot] = 0;
-  RTB_CUDA(cudaMalloc(&s->d_frame[slot], bytes));
-  s->frame_cap[slot] = bytes;
+int ensure_frame(int slot, size_t bytes) {
+  if (g_rtb.frame_cap[slot] >= bytes) return RTB_OK;
+  if (g_rtb.d_frame[slot]) cudaFree(g_rtb.d_frame[slot]);
+  g_rtb.d_frame[slot] = nullptr; g_rtb.frame_cap[slot] = 0;
+  RTB_CUDA(cudaMalloc(&g_rtb.d_frame[slot], bytes));
+  g_rtb.frame_cap[slot] = bytes;
   return RTB_OK;
 }
 
@@ -305,6 +305,7 @@ int rtb_init(int device) {
     RTB_CUDA(cudaEventCreateWithFlags(&g_rtb.frame_done[i], cudaEventDisableTiming));
     RTB_CUDA(cudaEventCreateWithFlags(&g_rtb.copy_done[i], cudaEventDisableTiming));
   }
+  RTB_CUDA(cudaMalloc(&g_rtb.d_counters, 3 * sizeof(unsigned long long)));
   g_rtb.inited = true;
   return RTB_OK;
 }
@@ -317,6 +318,10 @@ void rtb_shutdown(void) {
   cudaEventDestroy(g_rtb.ev0); cudaEventDestroy(g_rtb.ev1);
   cudaEventDestroy(g_rtb.ev2); cudaEventDestroy(g_rtb.ev3);
   for (int i = 0; i < 2; i++) { cudaEventDestroy(g_rtb.frame_done[i]); cudaEventDestroy(g_rtb.copy_done[i]); }
+  for (int i = 0; i < g_rtb.n_timers; i++) cudaEventDestroy(g_rtb.timers[i]);
+  cudaFree(g_rtb.d_frame[0]); cudaFree(g_rtb.d_frame[1]); cudaFree(g_rtb.d_counters);
+  wf_free();
+  (void)cudaGetLastError();
   g_rtb = RtbGlobal{};
 }
 
@@ -388,7 +393,6 @@ int rtb_scene_create(const RtbSceneDesc* d, rtb_scene_t* out) {
   }
   RTB_CUDA(cudaMalloc(&s->d_primary_tab, (size_t)na * sizeof(float4)));
   RTB_CUDA(cudaMallocHost(&s->h_primary_tab, (size_t)na * sizeof(float4)));
-  RTB_CUDA(cudaMalloc(&s->d_counters, 3 * sizeof(unsigned long long)));
   guard.s = nullptr;
   *out = s;
   return RTB_OK;
@@ -402,9 +406,6 @@ void rtb_scene_destroy(rtb_scene_t s) {
   for (int k = 0; k < RTB_MAX_LIGHTS; k++) cudaFree(s->d_light_tab[k]);
   cudaFree(s->d_primary_tab);
   if (s->h_primary_tab) cudaFreeHost(s->h_primary_tab);
-  cudaFree(s->d_frame[0]); cudaFree(s->d_frame[1]);
-  cudaFree(s->d_counters);
-  wf_free(s);
   (void)cudaGetLastError();
   delete s;
 }
@@ -431,16 +432,16 @@ int rtb_render(rtb_scene_t s, const RtbCamera* cam, const RtbRenderOpts* o, uint
   int rc = validate_render(s, cam, o, out);
   if (rc != RTB_OK) return rc;
   const size_t bytes = (size_t)cam->width * cam->height * 4;
-  rc = ensure_frame(s, 0, bytes);
+  rc = ensure_frame(0, bytes);
   if (rc != RTB_OK) return rc;
   cudaStream_t st = g_rtb.stream;
   if (stats) memset(stats, 0, sizeof *stats);
   RTB_CUDA(cudaEventRecord(g_rtb.ev0, st));
-  rc = render_to_device(s, cam, o, s->d_frame[0], st, stats);
+  rc = render_to_device(s, cam, o, g_rtb.d_frame[0], st, stats);
   if (rc != RTB_OK) return rc;
   RTB_CUDA(cudaEventRecord(g_rtb.ev1, st));
   const RowMap rm = make_rowmap(cam, o);
-  rc = copy_rows_to_host(rm, s->d_frame[0], out, cam->height, st);
+  rc = copy_rows_to_host(rm, g_rtb.d_frame[0], out, cam->height, st);
   if (rc != RTB_OK) return rc;
   RTB_CUDA(cudaEventRecord(g_rtb.ev2, st));
   RTB_CUDA(cudaEventSynchronize(g_rtb.ev2));
@@ -472,20 +473,22 @@ int rtb_render_batch(rtb_scene_t s, const RtbCamera* cams, int32_t nframes, cons
     if (rc != RTB_OK) return rc;
     const int slot = f & 1;
     const size_t bytes = (size_t)cams[f].width * cams[f].height * 4;
-    rc = ensure_frame(s, slot, bytes);
+    rc = ensure_frame(slot, bytes);
     if (rc != RTB_OK) return rc;
     if (f >= 2) RTB_CUDA(cudaStreamWaitEvent(g_rtb.stream, g_rtb.copy_done[slot], 0));
     RtbStats one;
     memset(&one, 0, sizeof one);
-    rc = render_to_device(s, &cams[f], o, s->d_frame[slot], g_rtb.stream, stats ? &one : nullptr);
+    rc = render_to_device(s, &cams[f], o, g_rtb.d_frame[slot], g_rtb.stream, stats ? &one : nullptr);
     if (rc != RTB_OK) return rc;
     if (stats) {
       stats->nodes += one.nodes; stats->shadow_rays += one.shadow_rays; stats->sphere_tests += one.sphere_tests;
       stats->launches += one.launches; stats->bands += one.bands;
+      stats->ms_trace_primary += one.ms_trace_primary; stats->ms_trace_secondary += one.ms_trace_secondary;
+      stats->ms_shadow += one.ms_shadow; stats->ms_compose += one.ms_compose;
     }
     RTB_CUDA(cudaEventRecord(g_rtb.frame_done[slot], g_rtb.stream));
     RTB_CUDA(cudaStreamWaitEvent(g_rtb.copy_stream, g_rtb.frame_done[slot], 0));
-    RTB_CUDA(cudaMemcpyAsync(out + off, s->d_frame[slot], bytes, cudaMemcpyDeviceToHost, g_rtb.copy_stream));
+    RTB_CUDA(cudaMemcpyAsync(out + off, g_rtb.d_frame[slot], bytes, cudaMemcpyDeviceToHost, g_rtb.copy_stream));
     RTB_CUDA(cudaEventRecord(g_rtb.copy_done[slot], g_rtb.copy_stream));
     off += bytes;
   }

@@ -56,12 +56,6 @@ struct RtbScene_ {
   float4* h_primary_tab = nullptr;        // pinned staging
   double primary_origin[3] = {0, 0, 0};
   bool primary_valid = false;
-  // per-scene output + workspace
-  uint8_t* d_frame[2] = {nullptr, nullptr};
-  size_t frame_cap[2] = {0, 0};
-  WfBuffers wf = {};
-  size_t wf_bytes = 0;
-  unsigned long long* d_counters = nullptr;   // 3 x u64 for the pixel kernels
 };
 
 struct RtbGlobal {
@@ -74,6 +68,18 @@ struct RtbGlobal {
   cudaStream_t stream = nullptr, copy_stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
   cudaEvent_t frame_done[2] = {nullptr, nullptr}, copy_done[2] = {nullptr, nullptr};
+  // library-owned output staging + wavefront workspace, shared by all scenes (one render in flight
+  // per process: the entry points serialise on a mutex), so creating a scene stays cheap
+  uint8_t* d_frame[2] = {nullptr, nullptr};
+  size_t frame_cap[2] = {0, 0};
+  WfBuffers wf = {};
+  int wf_lights = 0;                          // shadow queues allocated
+  size_t wf_bytes = 0;
+  unsigned long long* d_counters = nullptr;   // 3 x u64 for the pixel kernels
+  // per-kernel-class event pool for RtbStats.ms_* (only used when stats are requested)
+  static const int kMaxTimers = 256;
+  cudaEvent_t timers[kMaxTimers] = {};
+  int n_timers = 0;
 };
 extern RtbGlobal g_rtb;
 
@@ -96,4 +102,4 @@ int launch_pixel_f32(const DevSceneT<float>& sc, const DevFrameT<float>& fr, con
 // wavefront pipeline: renders the rows of `rm` into d_out, splitting into bands as needed.
 int wf_render(RtbScene_* s, const RtbCamera* cam, const DevFrameT<float>& fr, const RowMap& rm,
               uint8_t* d_out, cudaStream_t st, RtbStats* stats, bool want_counts);
-void wf_free(RtbScene_* s);
+void wf_free();

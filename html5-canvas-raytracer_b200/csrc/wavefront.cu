@@ -20,6 +20,8 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <vector>
 #include "rtb_internal.h"
 #include "pixel_kernel.cuh"   // primary_ray<>
 
@@ -473,38 +475,43 @@ size_t per_node_bytes(int n_lights) {
   return 16 * 7 + 8 + (n_lights > 2 ? 16 : 0) + 4 * (size_t)n_lights;
 }
 
-int ensure_workspace(RtbScene_* s, uint32_t cap_nodes) {
-  WfBuffers& b = s->wf;
-  if (b.cap_nodes >= cap_nodes && b.ctr) return RTB_OK;
-  wf_free(s);
-  const size_t n = cap_nodes;
+int ensure_workspace(int n_lights, uint32_t cap_nodes) {
+  WfBuffers& b = g_rtb.wf;
+  const bool need_lq2 = n_lights > 2;
+  if (b.cap_nodes >= cap_nodes && b.ctr && g_rtb.wf_lights >= n_lights && (!need_lq2 || b.lq2)) return RTB_OK;
+  const uint32_t cap = std::max(cap_nodes, b.cap_nodes);
+  const int lights = std::max(n_lights, g_rtb.wf_lights);
+  wf_free();
+  const size_t n = cap;
   RTB_CUDA(cudaMalloc(&b.ray_o, n * 16));
   RTB_CUDA(cudaMalloc(&b.ray_d, n * 16));
   RTB_CUDA(cudaMalloc(&b.link, n * 8));
   RTB_CUDA(cudaMalloc(&b.pos, n * 16));
   RTB_CUDA(cudaMalloc(&b.base, n * 16));
   RTB_CUDA(cudaMalloc(&b.lq, n * 16));
-  if (s->n_lights > 2) RTB_CUDA(cudaMalloc(&b.lq2, n * 16));
+  if (lights > 2) RTB_CUDA(cudaMalloc(&b.lq2, n * 16));
   RTB_CUDA(cudaMalloc(&b.acc, n * 16));
   RTB_CUDA(cudaMalloc(&b.child_a, n * 16));
   RTB_CUDA(cudaMalloc(&b.child_b, n * 16));
-  for (int k = 0; k < s->n_lights; k++) RTB_CUDA(cudaMalloc(&b.sq[k], n * 4));
+  for (int k = 0; k < lights; k++) RTB_CUDA(cudaMalloc(&b.sq[k], n * 4));
   RTB_CUDA(cudaMalloc(&b.ctr, sizeof(WfCounters) + sizeof(WfSticky)));
-  b.cap_nodes = cap_nodes;
-  s->wf_bytes = n * per_node_bytes(s->n_lights);
+  b.cap_nodes = cap;
+  g_rtb.wf_lights = lights;
+  g_rtb.wf_bytes = n * per_node_bytes(lights);
   return RTB_OK;
 }
 
 }  // namespace
 
-void wf_free(RtbScene_* s) {
-  WfBuffers& b = s->wf;
+void wf_free() {
+  WfBuffers& b = g_rtb.wf;
   cudaFree(b.ray_o); cudaFree(b.ray_d); cudaFree(b.link); cudaFree(b.pos); cudaFree(b.base);
   cudaFree(b.lq); cudaFree(b.lq2); cudaFree(b.acc); cudaFree(b.child_a); cudaFree(b.child_b);
   for (int k = 0; k < RTB_MAX_LIGHTS; k++) cudaFree(b.sq[k]);
   cudaFree(b.ctr);
   b = WfBuffers{};
-  s->wf_bytes = 0;
+  g_rtb.wf_lights = 0;
+  g_rtb.wf_bytes = 0;
 }
 
 int wf_render(RtbScene_* s, const RtbCamera* cam, const DevFrameT<float>& fr32, const RowMap& rm,
@@ -550,9 +557,9 @@ int wf_render(RtbScene_* s, const RtbCamera* cam, const DevFrameT<float>& fr32, 
   if (const char* e = getenv("RTB_WF_CAP_NODES")) { const long long v = atoll(e); if (v > 0) cap = (uint64_t)v; }
   if (cap < 4 * sub_per_row) cap = 4 * sub_per_row;      // at least one row per band with headroom
   if (cap > 0xfffffff0ull) { rtb_set_error("frame too wide for the wavefront queues"); return RTB_ERR_UNSUPPORTED; }
-  int rc = ensure_workspace(s, (uint32_t)cap);
+  int rc = ensure_workspace(s->n_lights, (uint32_t)cap);
   if (rc != RTB_OK) return rc;
-  cap = s->wf.cap_nodes;
+  cap = g_rtb.wf.cap_nodes;
 
   WfParams P;
   memset(&P, 0, sizeof P);
@@ -567,8 +574,9 @@ int wf_render(RtbScene_* s, const RtbCamera* cam, const DevFrameT<float>& fr32, 
   }
   f.projW = cam->projW; f.projH = cam->projH; f.projD = cam->projD;
   P.rm = rm;
-  P.b = s->wf;
-  P.sticky = reinterpret_cast<WfSticky*>(reinterpret_cast<char*>(s->wf.ctr) + sizeof(WfCounters));
+  P.b = g_rtb.wf;
+  if (s->n_lights <= 2) P.b.lq2 = nullptr;                 // kernels key the lights-2/3 store on this
+  P.sticky = reinterpret_cast<WfSticky*>(reinterpret_cast<char*>(g_rtb.wf.ctr) + sizeof(WfCounters));
   P.geom = reinterpret_cast<const float4*>(s->d_geom32);
   P.primary_tab = s->d_primary_tab;
   for (int k = 0; k < s->n_lights; k++) P.light_tab[k] = s->d_light_tab[k];
@@ -595,31 +603,51 @@ int wf_render(RtbScene_* s, const RtbCamera* cam, const DevFrameT<float>& fr32, 
   int rows_per_band = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)n_rows, (cap / 3) / sub_per_row));
   WfSticky h_sticky;
   uint32_t launches = 0, bands = 0;
+  // per-class timing (stats only): an event after every class of every band, classes tagged
+  enum { T_START = 0, T_PRIMARY, T_SECONDARY, T_SHADOW, T_COMPOSE };
+  std::vector<int> tags;
+  auto mark = [&](int tag) -> int {
+    if (!stats) return RTB_OK;
+    if ((int)tags.size() >= RtbGlobal::kMaxTimers) return RTB_OK;   // long band lists: later bands untimed
+    if ((int)tags.size() >= g_rtb.n_timers) {
+      RTB_CUDA(cudaEventCreate(&g_rtb.timers[g_rtb.n_timers]));
+      g_rtb.n_timers++;
+    }
+    RTB_CUDA(cudaEventRecord(g_rtb.timers[tags.size()], st));
+    tags.push_back(tag);
+    return RTB_OK;
+  };
   for (int attempt = 0;; attempt++) {
     launches = 0; bands = 0;
+    tags.clear();
     RTB_CUDA(cudaMemsetAsync(P.sticky, 0, sizeof(WfSticky), st));
     for (int l0 = 0; l0 < n_rows; l0 += rows_per_band) {
       P.band_l0 = l0;
       P.band_rows = std::min(rows_per_band, n_rows - l0);
       P.n_sub = (uint32_t)((uint64_t)P.band_rows * sub_per_row);
       bands++;
-      RTB_CUDA(cudaMemsetAsync(s->wf.ctr, 0, sizeof(WfCounters), st));
+      RTB_CUDA(cudaMemsetAsync(g_rtb.wf.ctr, 0, sizeof(WfCounters), st));
+      if ((rc = mark(T_START)) != RTB_OK) return rc;
       wf_trace_kernel<true><<<grid_p, WF_THREADS, smem, st>>>(P, 1);
       launches++;
+      if ((rc = mark(T_PRIMARY)) != RTB_OK) return rc;
       for (int L = 2; L <= fr32.segs; L++) {
         wf_trace_kernel<false><<<grid_s, WF_THREADS, smem, st>>>(P, L);
         launches++;
       }
+      if ((rc = mark(T_SECONDARY)) != RTB_OK) return rc;
       for (int k = 0; k < s->n_lights; k++) {
         wf_shadow_kernel<<<grid_l, WF_THREADS, smem, st>>>(P, k);
         launches++;
       }
+      if ((rc = mark(T_SHADOW)) != RTB_OK) return rc;
       for (int L = fr32.segs; L >= 2; L--) {
         wf_compose_kernel<<<grid_c, WF_THREADS, 0, st>>>(P, L);
         launches++;
       }
       wf_resolve_kernel<<<grid_c, WF_THREADS, 0, st>>>(P, d_out);
       launches++;
+      if ((rc = mark(T_COMPOSE)) != RTB_OK) return rc;
       RTB_CUDA(cudaGetLastError());
     }
     RTB_CUDA(cudaMemcpyAsync(&h_sticky, P.sticky, sizeof h_sticky, cudaMemcpyDeviceToHost, st));
@@ -638,6 +666,15 @@ int wf_render(RtbScene_* s, const RtbCamera* cam, const DevFrameT<float>& fr32, 
     stats->sphere_tests += h_sticky.sphere_tests;
     stats->launches += launches;
     stats->bands += bands;
+    for (size_t i = 1; i < tags.size(); i++) {
+      if (tags[i] == T_START) continue;
+      float ms = 0.f;
+      RTB_CUDA(cudaEventElapsedTime(&ms, g_rtb.timers[i - 1], g_rtb.timers[i]));
+      if (tags[i] == T_PRIMARY) stats->ms_trace_primary += ms;
+      else if (tags[i] == T_SECONDARY) stats->ms_trace_secondary += ms;
+      else if (tags[i] == T_SHADOW) stats->ms_shadow += ms;
+      else stats->ms_compose += ms;
+    }
   }
   return RTB_OK;
 }

@@ -155,6 +155,11 @@ typedef struct RtbStats {
   uint64_t sphere_tests;     /* ray-sphere tests the DEVICE executed (<= reference's count)      */
   uint32_t launches;         /* kernel launches issued                                           */
   uint32_t bands;            /* row bands the frame was split into (wavefront queues)            */
+  /* CUDA-event time per kernel class of the wavefront pipeline (0 for the per-pixel kernels):   */
+  double ms_trace_primary;   /* level-1 closest-hit sweep + hit processing                       */
+  double ms_trace_secondary; /* levels >= 2 (reflect / refract rays)                             */
+  double ms_shadow;          /* occluder sweeps, all lights                                      */
+  double ms_compose;         /* post-order compose + RGBA8 resolve                               */
 } RtbStats;
 
 typedef struct RtbScene_* rtb_scene_t;

@@ -220,3 +220,24 @@ def test_empty_scene_is_red(rt, oracle):
         img = r.redraw(cam, precision=prec)
         assert (img.reshape(-1, 4) == np.array([255, 0, 0, 255], np.uint8)).all()
     r.close()
+
+
+def test_c3_full_size_sampled_rows(rt, oracle):
+    """BASELINE config 3 at its full size (3840x2160, 1024 spheres, segs 8): the GPU renders the whole
+    frame, the oracle every 54th row (40 rows) of it — the +-LSB gates must hold there too."""
+    objs = rt.scenes.synth_objects(1024, 1024)
+    cam = rt.scenes.demo_camera(3840, 2160)
+    step = 54
+    with rt.Renderer(objs) as r:
+        ref, cnt = oracle.render(r.desc, cam, rt.make_opts(segs=8), row_step=step)
+        rows = list(range(0, 2160, step))
+        img32, st = r.redraw(cam, stats=True, segs=8, kernel=rt.RTB_KERNEL_WAVEFRONT)
+        s32 = lsb_stats(img32[rows], ref[rows])
+        print("C3 4K fp32 wavefront on", len(rows), "rows:", s32, "kernel ms", st.kernel_ms, "bands", st.bands)
+        assert s32["within2"] >= FP32_WITHIN2 and s32["psnr"] >= FP32_PSNR_DB
+        img64 = np.zeros_like(img32)
+        for y in rows:   # fp64 validation kernel on exactly those rows (progressive row hand-back)
+            r.redraw(cam, out=img64, segs=8, precision=rt.RTB_PRECISION_FP64, y0=y, y1=y + 1)
+        s64 = lsb_stats(img64[rows], ref[rows])
+        print("C3 4K fp64 on", len(rows), "rows:", s64)
+        assert s64["within1"] >= FP64_WITHIN1 and s64["psnr"] >= FP64_PSNR_DB
