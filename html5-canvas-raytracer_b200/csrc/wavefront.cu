@@ -559,7 +559,8 @@ int wf_render(RtbScene_* s, const RtbCamera* cam, const DevFrameT<float>& fr32, 
   if (cap > 0xfffffff0ull) { rtb_set_error("frame too wide for the wavefront queues"); return RTB_ERR_UNSUPPORTED; }
   int rc = ensure_workspace(s->n_lights, (uint32_t)cap);
   if (rc != RTB_OK) return rc;
-  cap = g_rtb.wf.cap_nodes;
+  // the shared workspace may be larger than this call asked for; band sizes and the overflow
+  // check follow the REQUESTED capacity so that results do not depend on earlier calls
 
   WfParams P;
   memset(&P, 0, sizeof P);
@@ -575,7 +576,8 @@ int wf_render(RtbScene_* s, const RtbCamera* cam, const DevFrameT<float>& fr32, 
   f.projW = cam->projW; f.projH = cam->projH; f.projD = cam->projD;
   P.rm = rm;
   P.b = g_rtb.wf;
-  if (s->n_lights <= 2) P.b.lq2 = nullptr;                 // kernels key the lights-2/3 store on this
+  P.b.cap_nodes = (uint32_t)cap;
+  if (s->n_lights <= 2) P.b.lq2 = nullptr;                // kernels key the lights-2/3 store on this
   P.sticky = reinterpret_cast<WfSticky*>(reinterpret_cast<char*>(g_rtb.wf.ctr) + sizeof(WfCounters));
   P.geom = reinterpret_cast<const float4*>(s->d_geom32);
   P.primary_tab = s->d_primary_tab;
