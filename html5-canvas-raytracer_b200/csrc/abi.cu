@@ -380,19 +380,23 @@ int rtb_scene_create(const RtbSceneDesc* d, rtb_scene_t* out) {
   fill_scene_view<float>(s->sc32, s, d, s->d_geom32, s->d_mtl32);
 
   // wavefront per-light tables (fp64 arithmetic, one rounding to fp32)
-  std::vector<float4> tab(na);
+  const int np = wf_pad(na);
+  s->n_pad = np;
+  std::vector<float4> tab(np), exact(np);
+  const size_t tb = (size_t)np * sizeof(float4);
   for (int k = 0; k < d->n_lights; k++) {
-    for (int i = 0; i < n; i++) {
-      const RtbSphere& sp = d->spheres[i];
-      const double L0 = sp.origin[0] - d->lights[k][0], L1 = sp.origin[1] - d->lights[k][1],
-                   L2 = sp.origin[2] - d->lights[k][2];
-      tab[i] = make_float4((float)L0, (float)L1, (float)L2, (float)((L0 * L0 + L1 * L1 + L2 * L2) - sp.r2));
-    }
-    RTB_CUDA(cudaMalloc(&s->d_light_tab[k], (size_t)na * sizeof(float4)));
-    RTB_CUDA(cudaMemcpy(s->d_light_tab[k], tab.data(), (size_t)na * sizeof(float4), cudaMemcpyHostToDevice));
+    wf_make_table(d->spheres, n, np, d->lights[k], tab.data(), exact.data());
+    RTB_CUDA(cudaMalloc(&s->d_light_tab[k], tb));
+    RTB_CUDA(cudaMalloc(&s->d_light_x[k], tb));
+    RTB_CUDA(cudaMemcpy(s->d_light_tab[k], tab.data(), tb, cudaMemcpyHostToDevice));
+    RTB_CUDA(cudaMemcpy(s->d_light_x[k], exact.data(), tb, cudaMemcpyHostToDevice));
   }
-  RTB_CUDA(cudaMalloc(&s->d_primary_tab, (size_t)na * sizeof(float4)));
-  RTB_CUDA(cudaMallocHost(&s->h_primary_tab, (size_t)na * sizeof(float4)));
+  wf_make_geom_table(d->spheres, n, np, tab.data());
+  RTB_CUDA(cudaMalloc(&s->d_geom_tab, tb));
+  RTB_CUDA(cudaMemcpy(s->d_geom_tab, tab.data(), tb, cudaMemcpyHostToDevice));
+  RTB_CUDA(cudaMalloc(&s->d_primary_tab, tb));
+  RTB_CUDA(cudaMalloc(&s->d_primary_x, tb));
+  RTB_CUDA(cudaMallocHost(&s->h_primary_tab, 2 * tb));
   guard.s = nullptr;
   *out = s;
   return RTB_OK;
@@ -403,8 +407,8 @@ void rtb_scene_destroy(rtb_scene_t s) {
   if (g_rtb.inited) cudaDeviceSynchronize();
   cudaFree(s->d_geom64); cudaFree(s->d_geom32); cudaFree(s->d_mtl64); cudaFree(s->d_mtl32);
   cudaFree(s->d_tex); cudaFree(s->d_texels);
-  for (int k = 0; k < RTB_MAX_LIGHTS; k++) cudaFree(s->d_light_tab[k]);
-  cudaFree(s->d_primary_tab);
+  for (int k = 0; k < RTB_MAX_LIGHTS; k++) { cudaFree(s->d_light_tab[k]); cudaFree(s->d_light_x[k]); }
+  cudaFree(s->d_geom_tab); cudaFree(s->d_primary_tab); cudaFree(s->d_primary_x);
   if (s->h_primary_tab) cudaFreeHost(s->h_primary_tab);
   (void)cudaGetLastError();
   delete s;

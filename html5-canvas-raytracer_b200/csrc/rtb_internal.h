@@ -17,6 +17,8 @@ struct WfCounters {          // one small device struct, zeroed per band
   uint32_t _pad;
   uint32_t level_end[RTB_MAX_SEGS + 1];   // level L = [level_end[L-1], level_end[L]); level_end[0] = 0
   uint32_t sq_count[RTB_MAX_LIGHTS];      // shadow queue fill per light
+  uint32_t work_trace[RTB_MAX_SEGS + 2];   // next chunk of level L (persistent-kernel work counters)
+  uint32_t work_shadow[RTB_MAX_LIGHTS];
   unsigned long long stat_nodes, stat_shadow, stat_tests;
 };
 
@@ -51,9 +53,13 @@ struct RtbScene_ {
   DevSceneT<float> sc32;
   // wavefront tables: per light (C - light, |C - light|^2 - r2), computed in fp64 once per scene;
   // the primary table (C - origin, |C - origin|^2 - r2) is rebuilt per camera.
-  float4* d_light_tab[RTB_MAX_LIGHTS] = {nullptr, nullptr, nullptr, nullptr};
-  float4* d_primary_tab = nullptr;
-  float4* h_primary_tab = nullptr;        // pinned staging
+  int n_pad = 0;                          // n_spheres rounded up to RTB_WF_GROUP
+  float4* d_geom_tab = nullptr;           // packed general-ray table (wf_make_geom_table)
+  float4* d_light_tab[RTB_MAX_LIGHTS] = {nullptr, nullptr, nullptr, nullptr};   // packed, per light
+  float4* d_light_x[RTB_MAX_LIGHTS] = {nullptr, nullptr, nullptr, nullptr};     // exact (L, c), per light
+  float4* d_primary_tab = nullptr;        // packed, per camera origin
+  float4* d_primary_x = nullptr;          // exact (L, c)
+  float4* h_primary_tab = nullptr;        // pinned staging: n_pad packed + n_pad exact float4
   double primary_origin[3] = {0, 0, 0};
   bool primary_valid = false;
 };
@@ -98,6 +104,50 @@ int launch_pixel_f64(const DevSceneT<double>& sc, const DevFrameT<double>& fr, c
                      uint8_t* d_out, unsigned long long* d_counters, cudaStream_t st, uint32_t* launches);
 int launch_pixel_f32(const DevSceneT<float>& sc, const DevFrameT<float>& fr, const RowMap& rm,
                      uint8_t* d_out, unsigned long long* d_counters, cudaStream_t st, uint32_t* launches);
+
+// Packed sweep tables of the wavefront kernels.  Spheres are stored in PAIRS so that one packed FP32
+// instruction (FFMA2, sm_100 f32x2) tests two spheres: pair p = spheres (2p, 2p+1) occupies
+//   tab[2p]   = (x0, x1, y0, y1)        tab[2p+1] = (z0, z1, w0, w1)
+// and the table is padded to a multiple of RTB_WF_GROUP spheres with dummies that never test positive.
+// A test value whose SIGN BIT IS SET marks a candidate; all table arithmetic is fp64, one rounding.
+//
+// wf_make_table — rays that all start at `org` (camera origin, or a light for the occluder sweeps):
+//   (x,y,z) = L = C - org,  w = sc = sqrt(|L|^2 - r2);  test value  sc - dir.L  <= 0  <=>  the line hits
+//   the sphere and the sphere is ahead of org.  sc is shrunk slightly so that fp32 rounding of the dot
+//   product can only ADD candidates (the slow path re-decides exactly).  org inside the sphere: -inf
+//   (always a candidate); dummy: +inf.   exact[i] = (L, |L|^2 - r2) for the slow path.
+// wf_make_geom_table — general rays: (x,y,z) = C, w = -r2 (1 + 2e-6); test value d2 - r2' (main.js:424-425).
+constexpr int RTB_WF_GROUP = 16;
+inline int wf_pad(int n) { return (n + RTB_WF_GROUP - 1) / RTB_WF_GROUP * RTB_WF_GROUP; }
+inline void wf_pack(float4* tab, int i, float x, float y, float z, float w) {
+  float* a = reinterpret_cast<float*>(&tab[2 * (i / 2)]);
+  float* b = reinterpret_cast<float*>(&tab[2 * (i / 2) + 1]);
+  const int h = i & 1;
+  a[h] = x; a[2 + h] = y; b[h] = z; b[2 + h] = w;
+}
+inline void wf_make_table(const RtbSphere* sp, int n, int n_pad, const double org[3], float4* tab, float4* exact) {
+  const float inf = __builtin_huge_valf();
+  for (int i = 0; i < n_pad; i++) {
+    if (i >= n) { wf_pack(tab, i, 0.f, 0.f, 0.f, inf); exact[i] = make_float4(0.f, 0.f, 0.f, inf); continue; }
+    const double L0 = sp[i].origin[0] - org[0], L1 = sp[i].origin[1] - org[1], L2 = sp[i].origin[2] - org[2];
+    const double cc = (L0 * L0 + L1 * L1 + L2 * L2) - sp[i].r2;
+    float sc = -inf;
+    if (cc > 0) {
+      const double len = __builtin_sqrt(L0 * L0 + L1 * L1 + L2 * L2);
+      sc = (float)(__builtin_sqrt(cc) * (1.0 - 1e-6) - 4e-7 * len);
+    }
+    wf_pack(tab, i, (float)L0, (float)L1, (float)L2, sc);
+    exact[i] = make_float4((float)L0, (float)L1, (float)L2, (float)cc);
+  }
+}
+inline void wf_make_geom_table(const RtbSphere* sp, int n, int n_pad, float4* tab) {
+  const float inf = __builtin_huge_valf();
+  for (int i = 0; i < n_pad; i++) {
+    if (i >= n) { wf_pack(tab, i, 0.f, 0.f, 0.f, inf); continue; }
+    wf_pack(tab, i, (float)sp[i].origin[0], (float)sp[i].origin[1], (float)sp[i].origin[2],
+            -(float)(sp[i].r2 * (1.0 + 2e-6)));
+  }
+}
 
 // wavefront pipeline: renders the rows of `rm` into d_out, splitting into bands as needed.
 int wf_render(RtbScene_* s, const RtbCamera* cam, const DevFrameT<float>& fr, const RowMap& rm,

@@ -1,22 +1,33 @@
 // wavefront.cu — fp32 THROUGHPUT path: the Whitted tree of main.js:220-337 evaluated
 // breadth-first over a whole row band instead of depth-first per pixel.
 //
-//   TRACE  level L : one ray per lane; closest-hit sweep over ALL spheres in array order from shared
-//                    memory (main.js:223-230), then the hit record, reflect/refract directions
+//   TRACE  level L : several rays per lane; closest-hit sweep over ALL spheres in array order from
+//                    shared memory (main.js:223-230), then the hit record, reflect/refract directions
 //                    (main.js:233-266), the sampler (main.js:320) and the occlusion-independent
 //                    part of the light loop (main.js:286-292, 306-313).  Live child rays and
 //                    shadow rays are compacted into queues with warp ballots (one atomic per warp).
 //   SHADOW light k : occluder sweep main.js:293-304 for every queued node, traced FROM the light so
-//                    that all rays of the launch share an origin: per-sphere constants
-//                    (C - light, |C - light|^2 - r2) are precomputed in fp64 and the per-test work
-//                    drops to 4 FP32 instructions.  The light_intensity carry-over
-//                    between lights (main.js:284, H1-b) is the queue hand-off k -> next facing light.
+//                    that all rays of the launch share an origin.  The light_intensity
+//                    carry-over between lights (main.js:284, H1-b) is the queue hand-off
+//                    k -> next facing light.
 //   COMPOSE level L: post-order clamp-compose main.js:322-336, deepest level first; each child
 //                    writes its colour (scaled by the parent's albedo[3|4]) into its parent; level 1
 //                    averages sub-samples and stores RGBA8 as uint4 (4 pixels per thread).
 //
-// Every level is a grid-stride kernel whose bounds are read from device counters, so a band is a
-// fixed launch sequence without host round trips.
+// The sweeps are written for the B200 SM as measured (tools/fp32_peak.cu, profiles/):
+//   * a warp-wide LDS.128 costs 4 LSU cycles even when all lanes read the same 16 bytes, so every
+//     sphere fetched from shared memory is tested against R rays held in registers (R = 8 for the
+//     shared-origin sweeps, 4 for general rays) — otherwise the kernel is LSU-bound, not FP32-bound;
+//   * tests run two spheres at a time on the packed FP32 pipe (FFMA2 / FADD2 / FMUL2, sm_100 f32x2):
+//     half the issue slots of scalar FFMA and no 3-source register-bank conflicts
+//     (measured: scalar dot-shaped FFMA 76 % of peak, FFMA2 89 %);
+//   * the fast path never branches per test: the sign bit of each test value is funnel-shifted into
+//     a per-ray mask (one ALU-pipe instruction, off the FMA pipe) and a group of 16 spheres ends with
+//     a single branch; the slow path visits exactly the set bits (exact discriminant, sqrt, the
+//     0.001 window of main.js:429-439) and keeps the closest hit as a (t, index) key.
+//
+// Every level is a persistent kernel that pulls fixed-size chunks from a device counter; bounds are
+// read from device counters too, so a band is a fixed launch sequence without host round trips.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -39,9 +50,14 @@ struct WfParams {
   RowMap rm;
   WfBuffers b;
   WfSticky* sticky;
-  const float4* geom;         // Cx, Cy, Cz, r2
-  const float4* primary_tab;  // C - origin, |C - origin|^2 - r2
+  const float4* geom;         // exact Cx, Cy, Cz, r2                                  (n_spheres)
+  // packed sweep tables (see wf_make_table): per sphere PAIR two float4, padded with never-hit dummies
+  const float4* geom_tab;     // (x0,x1,y0,y1) (z0,z1,-r2_0',-r2_1')
+  const float4* primary_tab;  // (Lx0,Lx1,Ly0,Ly1) (Lz0,Lz1,sc0,sc1), L = C - origin
   const float4* light_tab[RTB_MAX_LIGHTS];
+  const float4* primary_x;    // exact (L, |L|^2 - r2) for the slow path               (n_spheres)
+  const float4* light_x[RTB_MAX_LIGHTS];
+  int32_t n_pad;
   float origin[3];
   int32_t band_l0;            // first local row of the band
   int32_t band_rows;
@@ -52,6 +68,12 @@ struct WfParams {
 
 constexpr int WF_THREADS = 256;
 constexpr float WF_INF = __builtin_huge_valf();
+constexpr int WF_GROUP = 8;              // spheres per candidate check; the unrolled body (4 sphere pairs x R
+                                         // rays) must stay well inside the ~6 KB L0 instruction cache
+static_assert(RTB_WF_GROUP % WF_GROUP == 0, "table padding must be a multiple of the sweep group");
+constexpr int R_SHARED = 8;              // rays per lane, shared-origin sweeps (primary, shadow)
+constexpr int R_GENERAL = 4;             // rays per lane, general sweep (reflect / refract rays)
+constexpr unsigned long long KEY_NONE = 0x7f800000ffffffffull;   // t = +inf, no sphere
 
 RTB_DEVINL uint32_t lanemask_lt() { uint32_t m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
 
@@ -80,219 +102,400 @@ RTB_DEVINL void publish_level(const WfParams& P, int level) {
   }
 }
 
+// Persistent-kernel work distribution: one atomic per warp per chunk.
+RTB_DEVINL uint32_t next_chunk(uint32_t* counter, uint32_t lane) {
+  uint32_t c = 0;
+  if (lane == 0) c = atomicAdd(counter, 1u);
+  return __shfl_sync(0xffffffffu, c, 0);
+}
+
+RTB_DEVINL float2 f2(float a, float b) { return make_float2(a, b); }
+// (mask << 1) | sign(v): one SHF on the ALU pipe
+RTB_DEVINL uint32_t push_sign(uint32_t mask, float v) { return __funnelshift_l(__float_as_uint(v), mask, 1); }
+// closest-hit key: (t bits, sphere index, flip) — min over keys == smallest t, then lowest index
+RTB_DEVINL unsigned long long hit_key(float t, int idx, bool flip) {
+  return ((unsigned long long)__float_as_uint(t) << 32) | ((uint32_t)idx << 1) | (flip ? 1u : 0u);
+}
+
+// Exact part of intersectSphere (main.js:426-439) from tca and the discriminant r2 - d2.
+RTB_DEVINL void exact_update(float tca, float disc, float eps, int jj, unsigned long long& best) {
+  if (disc >= 0.f) {
+    const float thc = sqrtf(disc);
+    const float t0 = tca - thc, t1 = tca + thc;
+    const float t = (t0 >= eps) ? t0 : ((t1 >= eps) ? t1 : WF_INF);
+    if (t < WF_INF) {
+      const unsigned long long k = hit_key(t, jj, t0 < eps);   // main.js:445: l flips when t0 < eps
+      if (k < best) best = k;
+    }
+  }
+}
+
+// ---- slow paths (out of line: the hot loops must stay small for the instruction cache) ----------------------
+// Visit exactly the candidate spheres of one ray in group j (mask bit b <-> sphere j + GROUP-1-b).
+__device__ __noinline__ unsigned long long slow_primary(const float4* __restrict__ exact, int j, uint32_t m,
+                                                        float ndx, float ndy, float ndz, float eps,
+                                                        unsigned long long best) {
+  while (m) {
+    const int b = 31 - __clz((int)m);
+    m ^= 1u << b;
+    const int jj = j + (8 - 1) - b;
+    const float4 x = __ldg(exact + jj);
+    const float tca = -(ndx * x.x + ndy * x.y + ndz * x.z);
+    exact_update(tca, tca * tca - x.w, eps, jj, best);
+  }
+  return best;
+}
+
+__device__ __noinline__ unsigned long long slow_general(const float4* __restrict__ geom, int j, uint32_t m,
+                                                        float nox, float noy, float noz, float dx, float dy,
+                                                        float dz, float eps, unsigned long long best) {
+  while (m) {
+    const int b = 31 - __clz((int)m);
+    m ^= 1u << b;
+    const int jj = j + (8 - 1) - b;
+    const float4 s = __ldg(geom + jj);
+    const float L0 = s.x + nox, L1 = s.y + noy, L2 = s.z + noz;
+    const float tca = dx * L0 + dy * L1 + dz * L2;
+    // d2 as |L - tca d|^2: no cancellation between |L|^2 and tca^2 for the r = 500 / 5000 spheres
+    const float v0 = L0 - tca * dx, v1 = L1 - tca * dy, v2 = L2 - tca * dz;
+    exact_update(tca, s.w - (v0 * v0 + v1 * v1 + v2 * v2), eps, jj, best);
+  }
+  return best;
+}
+
+// Occluders of one shadow ray among the candidates of group j; returns the updated light_intensity
+// (main.js:297-302).  t runs along the reference's ray (hit.p -> light): t = len - s.
+__device__ __noinline__ float slow_shadow(const float4* __restrict__ exact, const DevMaterial<float>* __restrict__ mtl,
+                                          int j, uint32_t m, float nwx, float nwy, float nwz, float len, int hit_i,
+                                          float eps, float I) {
+  while (m) {
+    const int b = 31 - __clz((int)m);
+    m ^= 1u << b;
+    const int jj = j + (8 - 1) - b;
+    if (jj == hit_i) continue;                              // main.js:294 — no shadow on self
+    const float4 x = __ldg(exact + jj);
+    const float tca = -(nwx * x.x + nwy * x.y + nwz * x.z);
+    const float disc = tca * tca - x.w;
+    if (disc >= 0.f) {
+      const float thc = sqrtf(disc);
+      const float t0 = len - (tca + thc), t1 = len - (tca - thc);
+      const float t = (t0 >= eps) ? t0 : ((t1 >= eps) ? t1 : WF_INF);
+      if (t < len) {
+        const float a4 = mtl[jj].albedo[4];
+        if (a4 != 0.f) I /= a4; else return 0.f;
+      }
+    }
+  }
+  return I;
+}
+
+// ---- sweeps ------------------------------------------------------------------------------------------------
+// Shared-origin closest hit (primary rays).  nd = -dir.  Fast test per sphere: sc - dir.L <= 0, i.e.
+// "the line hits the sphere and the sphere is ahead" (sc = sqrt(|L|^2 - r2), fp64 on the host, -inf
+// when the origin is inside).  3 FFMA2 per sphere pair per ray.
+template <int R>
+RTB_DEVINL void sweep_primary(const float4* __restrict__ tab, const float4* __restrict__ exact, int n_pad,
+                              const float (&nd)[R][3], const bool (&active)[R], unsigned long long (&best)[R],
+                              float eps) {
+  uint32_t mask[R];
+#pragma unroll
+  for (int q = 0; q < R; q++) { best[q] = KEY_NONE; mask[q] = 0; }
+  for (int j = 0; j < n_pad; j += WF_GROUP) {
+#pragma unroll
+    for (int u = 0; u < WF_GROUP / 2; u++) {
+      const float4 A = tab[j + 2 * u], B = tab[j + 2 * u + 1];
+#pragma unroll
+      for (int q = 0; q < R; q++) {
+        float2 t = __ffma2_rn(f2(nd[q][2], nd[q][2]), f2(B.x, B.y), f2(B.z, B.w));
+        t = __ffma2_rn(f2(nd[q][1], nd[q][1]), f2(A.z, A.w), t);
+        t = __ffma2_rn(f2(nd[q][0], nd[q][0]), f2(A.x, A.y), t);
+        mask[q] = push_sign(push_sign(mask[q], t.x), t.y);
+      }
+    }
+    uint32_t any = 0;
+#pragma unroll
+    for (int q = 0; q < R; q++) any |= mask[q];
+    if (any & 0xffu) {
+#pragma unroll
+      for (int q = 0; q < R; q++) {
+        const uint32_t m = mask[q] & 0xffu;
+        if (m && active[q]) best[q] = slow_primary(exact, j, m, nd[q][0], nd[q][1], nd[q][2], eps, best[q]);
+      }
+    }
+  }
+}
+
+// General closest hit (reflect / refract rays): the reference's test d2 = |L|^2 - tca^2 <= r2
+// (main.js:422-425), two spheres per packed instruction: 3 FADD2 + 7 FFMA2/FMUL2 per pair per ray.
+template <int R>
+RTB_DEVINL void sweep_general(const float4* __restrict__ tab, const float4* __restrict__ geom, int n_pad,
+                              const float (&no)[R][3], const float (&d)[R][3], const bool (&active)[R],
+                              unsigned long long (&best)[R], float eps) {
+  uint32_t mask[R];
+#pragma unroll
+  for (int q = 0; q < R; q++) { best[q] = KEY_NONE; mask[q] = 0; }
+  for (int j = 0; j < n_pad; j += WF_GROUP) {
+#pragma unroll
+    for (int u = 0; u < WF_GROUP / 2; u++) {
+      const float4 A = tab[j + 2 * u], B = tab[j + 2 * u + 1];
+#pragma unroll
+      for (int q = 0; q < R; q++) {
+        const float2 L0 = __fadd2_rn(f2(A.x, A.y), f2(no[q][0], no[q][0]));   // C - org
+        const float2 L1 = __fadd2_rn(f2(A.z, A.w), f2(no[q][1], no[q][1]));
+        const float2 L2 = __fadd2_rn(f2(B.x, B.y), f2(no[q][2], no[q][2]));
+        float2 tca = __fmul2_rn(f2(d[q][2], d[q][2]), L2);
+        tca = __ffma2_rn(f2(d[q][1], d[q][1]), L1, tca);
+        tca = __ffma2_rn(f2(d[q][0], d[q][0]), L0, tca);
+        float2 e = __ffma2_rn(L2, L2, f2(B.z, B.w));                          // |L|^2 - r2'
+        e = __ffma2_rn(L1, L1, e);
+        e = __ffma2_rn(L0, L0, e);
+        e = __ffma2_rn(f2(-tca.x, -tca.y), tca, e);                           // d2 - r2' <= 0: candidate
+        mask[q] = push_sign(push_sign(mask[q], e.x), e.y);
+      }
+    }
+    uint32_t any = 0;
+#pragma unroll
+    for (int q = 0; q < R; q++) any |= mask[q];
+    if (any & 0xffu) {
+#pragma unroll
+      for (int q = 0; q < R; q++) {
+        const uint32_t m = mask[q] & 0xffu;
+        if (m && active[q])
+          best[q] = slow_general(geom, j, m, no[q][0], no[q][1], no[q][2], d[q][0], d[q][1], d[q][2], eps, best[q]);
+      }
+    }
+  }
+}
+
+// ---- per-node work after the sweep ---------------------------------------------------------------------------
+struct WfRay {
+  float o[3], d[3];
+  uint32_t node, path, pixsub;
+  int segs_left;
+  bool active;
+};
+
+// Everything intersectWorld does with the closest hit except the occluder sweeps and the final
+// compose: hit record (main.js:441-447), reflect / refract directions (233-266), sampler (320), the
+// occlusion-independent light terms (286-292, 306-313); then warp-compacted queue pushes.
+// Must be called by all 32 lanes together (ballots inside).
+__device__ __noinline__ void process_hit(const WfParams& P, const WfRay& r, unsigned long long key, uint32_t lane) {
+  const bool active = r.active;
+  const uint32_t node = r.node;
+  const float* o = r.o;
+  const float* d = r.d;
+  const float best = __uint_as_float((uint32_t)(key >> 32));
+  const int hit_i = (best < WF_INF) ? (int)(((uint32_t)key) >> 1) : -1;
+  const bool flip = (key & 1ull) != 0;
+  const int W = P.fr64.width;
+  bool want_refl = false, want_refr = false;
+  float p[3] = {0.f, 0.f, 0.f}, rdir[3] = {0.f, 0.f, 0.f}, fdir[3] = {0.f, 0.f, 0.f};
+  float w_refl = 0.f, w_refr = 0.f;
+  int first_light = -1;
+  if (active) {
+    if (hit_i < 0) {                                      // main.js:231
+      P.b.pos[node] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+      P.b.base[node] = make_float4(1.f, 0.f, 0.f, __int_as_float(0));
+    } else {
+      const float4 g = __ldg(P.geom + hit_i);
+      const DevMaterial<float>& m = P.sc.mtl[hit_i];
+      p[0] = o[0] + d[0] * best; p[1] = o[1] + d[1] * best; p[2] = o[2] + d[2] * best;
+      float nn[3] = {p[0] - g.x, p[1] - g.y, p[2] - g.z};
+      const float nl = sqrtf(nn[0] * nn[0] + nn[1] * nn[1] + nn[2] * nn[2]);
+      if (nl != 0.f) { const float q = 1.f / nl; nn[0] *= q; nn[1] *= q; nn[2] *= q; }
+      const float l[3] = {flip ? -nn[0] : nn[0], flip ? -nn[1] : nn[1], flip ? -nn[2] : nn[2]};
+      const float a1 = m.albedo[1], a2 = m.albedo[2], a3 = m.albedo[3], a4 = m.albedo[4];
+      const float dn = d[0] * nn[0] + d[1] * nn[1] + d[2] * nn[2];
+      if (a3 > 0.f) {                                     // main.js:233-239
+        const float tt = -(2.f * dn);
+        rdir[0] = d[0] + nn[0] * tt; rdir[1] = d[1] + nn[1] * tt; rdir[2] = d[2] + nn[2] * tt;
+        const float len = sqrtf(rdir[0] * rdir[0] + rdir[1] * rdir[1] + rdir[2] * rdir[2]);
+        if (len != 0.f) {
+          const float q = 1.f / len; rdir[0] *= q; rdir[1] *= q; rdir[2] *= q;
+          want_refl = r.segs_left > 1;                    // a child with segs == 0 returns [0,0,0]
+          w_refl = a3;
+        }
+      }
+      if (a4 > 0.f) {                                     // main.js:241-266
+        float norm[3], eta;
+        float cosi = -js_max<float>(-1.f, js_min<float>(1.f, dn));
+        if (cosi < 0.f) { cosi = -cosi; norm[0] = -nn[0]; norm[1] = -nn[1]; norm[2] = -nn[2]; eta = m.refract_index; }
+        else { norm[0] = nn[0]; norm[1] = nn[1]; norm[2] = nn[2]; eta = 1.f / m.refract_index; }
+        const float k = 1.f - eta * eta * (1.f - cosi * cosi);
+        if (k > 0.f) {
+          const float q = eta * cosi - sqrtf(k);
+          fdir[0] = d[0] * eta + norm[0] * q; fdir[1] = d[1] * eta + norm[1] * q; fdir[2] = d[2] * eta + norm[2] * q;
+        } else {
+          const float tt = -(2.f * (d[0] * norm[0] + d[1] * norm[1] + d[2] * norm[2]));
+          fdir[0] = d[0] + norm[0] * tt; fdir[1] = d[1] + norm[1] * tt; fdir[2] = d[2] + norm[2] * tt;
+        }
+        const float len = sqrtf(fdir[0] * fdir[0] + fdir[1] * fdir[1] + fdir[2] * fdir[2]);
+        if (len != 0.f) {
+          const float q = 1.f / len; fdir[0] *= q; fdir[1] *= q; fdir[2] *= q;
+          want_refr = r.segs_left > 1;
+          w_refr = a4;
+        }
+      }
+      // sampler (main.js:320); u,v only matter to the texture sampler
+      float u = 0.f, v = 0.f, rgb[3];
+      if (m.sampler_kind == RTB_SAMPLER_TEXTURE) {
+        u = atan2f(-nn[2], -nn[0]) / 3.14159265358979323846f / 2.f + 0.5f;
+        v = asinf(-nn[1]) / (3.14159265358979323846f / 2.f) / 2.f + 0.5f;
+      }
+      uint32_t px = 0, py = 0, sub = 0;
+      if (m.sampler_kind == RTB_SAMPLER_STARS && P.fr64.star_mode == RTB_STARS_HASH) {
+        const uint32_t pix = r.pixsub / (uint32_t)P.spp;   // star hash key: pixel, sub-sample, path
+        sub = r.pixsub - pix * (uint32_t)P.spp;
+        px = pix % (uint32_t)W;
+        py = (uint32_t)P.rm.local_to_y(P.band_l0 + (int)(pix / (uint32_t)W));
+      }
+      run_sampler<float>(P.sc, m, nn, u, v, P.fr64.star_mode, P.fr64.star_seed, px, py, sub, r.path, rgb);
+      // occlusion-independent light terms (main.js:286-292, 306-313)
+      uint32_t mask = 0;
+      float q[RTB_MAX_LIGHTS] = {0.f, 0.f, 0.f, 0.f}, sp[RTB_MAX_LIGHTS] = {0.f, 0.f, 0.f, 0.f};
+      if (a1 > 0.f || a2 > 0.f) {
+        for (int k = 0; k < P.sc.n_lights; k++) {
+          float sv[3] = {P.sc.lights[k][0] - p[0], P.sc.lights[k][1] - p[1], P.sc.lights[k][2] - p[2]};
+          const float mag = sv[0] * sv[0] + sv[1] * sv[1] + sv[2] * sv[2];
+          const float len = sqrtf(mag);
+          if (len != 0.f) { const float qq = 1.f / len; sv[0] *= qq; sv[1] *= qq; sv[2] *= qq; }
+          const float sdot = sv[0] * l[0] + sv[1] * l[1] + sv[2] * l[2];
+          if (!(sdot > 0.f)) continue;
+          mask |= 1u << k;
+          q[k] = sdot / mag;
+          if (a2 > 0.f) {
+            // light_ref = normal3D(reflect3D(-sv, l)); spec_dot = dir . (-light_ref)
+            const float tt = 2.f * sdot;                   // -(2 * dot(-sv, l))
+            float lr[3] = {-sv[0] + l[0] * tt, -sv[1] + l[1] * tt, -sv[2] + l[2] * tt};
+            const float ll = sqrtf(lr[0] * lr[0] + lr[1] * lr[1] + lr[2] * lr[2]);
+            if (ll != 0.f) { const float qq = 1.f / ll; lr[0] *= qq; lr[1] *= qq; lr[2] *= qq; }
+            const float sd = -(d[0] * lr[0] + d[1] * lr[1] + d[2] * lr[2]);
+            if (sd > 0.f) sp[k] = powf(sd, m.specular_exponent);
+          }
+        }
+      }
+      if (mask) first_light = __ffs((int)mask) - 1;
+      P.b.pos[node] = make_float4(p[0], p[1], p[2], __int_as_float(hit_i));
+      P.b.base[node] = make_float4(rgb[0], rgb[1], rgb[2], __int_as_float((int)mask));
+      P.b.lq[node] = make_float4(q[0], sp[0], q[1], sp[1]);
+      if (P.b.lq2) P.b.lq2[node] = make_float4(q[2], sp[2], q[3], sp[3]);
+      P.b.acc[node] = make_float4(P.sc.light_intensity, 0.f, 0.f, 0.f);
+    }
+    P.b.child_a[node] = make_float4(0.f, 0.f, 0.f, 0.f);
+    P.b.child_b[node] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+
+  // ---- warp-compacted child allocation (north star: ballot/shuffle compaction of live rays) ---------
+  const uint32_t b1 = __ballot_sync(0xffffffffu, want_refl);
+  const uint32_t b2 = __ballot_sync(0xffffffffu, want_refr);
+  const uint32_t total = __popc(b1) + __popc(b2);
+  if (total) {
+    uint32_t cbase = 0;
+    if (lane == 0) cbase = atomicAdd(&P.b.ctr->node_count, total);
+    cbase = __shfl_sync(0xffffffffu, cbase, 0) + P.n_sub;
+    if (want_refl) {
+      const uint32_t c = cbase + __popc(b1 & lanemask_lt());
+      if (c < P.b.cap_nodes) {
+        P.b.ray_o[c] = make_float4(p[0], p[1], p[2], rdir[0]);
+        P.b.ray_d[c] = make_float4(rdir[1], rdir[2], w_refl, __uint_as_float(r.pixsub));
+        P.b.link[c] = make_int2((int)node, (int)((2u * r.path) | ((uint32_t)(r.segs_left - 1) << 24)));
+      } else { P.b.ctr->overflow = 1u; P.sticky->overflow = 1u; }
+    }
+    if (want_refr) {
+      const uint32_t c = cbase + __popc(b1) + __popc(b2 & lanemask_lt());
+      if (c < P.b.cap_nodes) {
+        P.b.ray_o[c] = make_float4(p[0], p[1], p[2], fdir[0]);
+        P.b.ray_d[c] = make_float4(fdir[1], fdir[2], w_refr, __uint_as_float(r.pixsub));
+        P.b.link[c] = make_int2((int)node, (int)((2u * r.path + 1u) | ((uint32_t)(r.segs_left - 1) << 24)));
+      } else { P.b.ctr->overflow = 1u; P.sticky->overflow = 1u; }
+    }
+  }
+  // ---- warp-compacted shadow queue push: first light that faces the surface -------------------------
+  for (int k = 0; k < P.sc.n_lights; k++) {
+    const uint32_t bk = __ballot_sync(0xffffffffu, first_light == k);
+    if (!bk) continue;
+    const int leader = __ffs((int)bk) - 1;
+    uint32_t qb = 0;
+    if ((int)lane == leader) qb = atomicAdd(&P.b.ctr->sq_count[k], (uint32_t)__popc(bk));
+    qb = __shfl_sync(0xffffffffu, qb, leader);
+    if (first_light == k) P.b.sq[k][qb + __popc(bk & lanemask_lt())] = node;
+  }
+}
+
 // ---- TRACE ----------------------------------------------------------------------------------------------
 template <bool PRIMARY>
 __global__ void __launch_bounds__(WF_THREADS)
 wf_trace_kernel(const __grid_constant__ WfParams P, int level) {
+  constexpr int R = PRIMARY ? R_SHARED : R_GENERAL;
   extern __shared__ float4 tab[];
-  const int n = P.sc.n_spheres;
+  const int n = P.sc.n_spheres, n_pad = P.n_pad;
   {
-    const float4* src = PRIMARY ? P.primary_tab : P.geom;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) tab[i] = src[i];
+    const float4* src = PRIMARY ? P.primary_tab : P.geom_tab;
+    for (int i = threadIdx.x; i < n_pad; i += blockDim.x) tab[i] = src[i];
   }
   __syncthreads();
   uint32_t begin, end;
   level_range(P, level, begin, end);
   const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
   const float eps = P.sc.eps;
   const int W = P.fr64.width;
   unsigned long long my_nodes = 0;
+  constexpr uint32_t CHUNK = 32u * R;
 
-  for (uint64_t base = (uint64_t)begin + (uint64_t)gwarp * 32u; base < end; base += (uint64_t)nwarps * 32u) {
-    const uint32_t node = (uint32_t)base + lane;
-    const bool active = node < end;
-    float o[3] = {0.f, 0.f, 0.f}, d[3] = {0.f, 0.f, 1.f};
-    int segs_left = 0;
-    uint32_t path = 1, px = 0, py = 0, sub = 0;
-    if (active) {
-      if (PRIMARY) {
-        const uint32_t pix = node / (uint32_t)P.spp;
-        sub = node - pix * (uint32_t)P.spp;
-        const int lrow = P.band_l0 + (int)(pix / (uint32_t)W);
-        px = pix % (uint32_t)W;
-        py = (uint32_t)P.rm.local_to_y(lrow);
-        const int g = P.fr64.spp_grid;
-        double ray[3];
-        primary_ray<double>(P.fr64, (int)px, (int)py, (int)(sub % g), (int)(sub / g), ray);
-        d[0] = (float)ray[0]; d[1] = (float)ray[1]; d[2] = (float)ray[2];
-        o[0] = P.origin[0]; o[1] = P.origin[1]; o[2] = P.origin[2];
-        segs_left = P.fr64.segs;
-      } else {
-        const float4 ro = P.b.ray_o[node], rd = P.b.ray_d[node];
-        const int2 lk = P.b.link[node];
-        o[0] = ro.x; o[1] = ro.y; o[2] = ro.z;
-        d[0] = ro.w; d[1] = rd.x; d[2] = rd.y;
-        path = (uint32_t)lk.y & 0xffffffu;
-        segs_left = (int)((uint32_t)lk.y >> 24);
-        // px/py/sub (star hash key) ride in the pixel id stored by the level-1 ancestor
-        const uint32_t pixsub = __float_as_uint(rd.w);
-        const uint32_t pix = pixsub / (uint32_t)P.spp;
-        sub = pixsub - pix * (uint32_t)P.spp;
-        px = pix % (uint32_t)W;
-        py = (uint32_t)P.rm.local_to_y(P.band_l0 + (int)(pix / (uint32_t)W));
-      }
-    }
-
-    // closest-hit sweep, array order, strict '<' keeps the lowest index on ties (main.js:229)
-    float best = WF_INF;
-    int hit_i = -1;
-    bool flip = false;
-    if (active) {
-      my_nodes++;
-#pragma unroll 4
-      for (int j = 0; j < n; j++) {
-        const float4 s = tab[j];
-        float tca, disc;
+  for (;;) {
+    const uint64_t base = (uint64_t)begin + (uint64_t)next_chunk(&P.b.ctr->work_trace[level], lane) * CHUNK;
+    if (base >= end) break;
+    float a[R][3], b[R][3];          // PRIMARY: a = -dir;  general: a = -org, b = dir
+    bool active[R];
+    unsigned long long best[R];
+#pragma unroll
+    for (int q = 0; q < R; q++) {
+      const uint32_t node = (uint32_t)base + (uint32_t)q * 32u + lane;
+      active[q] = node < end;
+      // idle slots must never look like candidates: zero direction (shared origin: test value = sc,
+      // positive unless the origin is inside the sphere) / far-away origin (general: d2 huge)
+      a[q][0] = a[q][1] = a[q][2] = PRIMARY ? 0.f : -3.0e18f;
+      b[q][0] = b[q][1] = b[q][2] = 0.f;
+      if (active[q]) {
+        my_nodes++;
         if (PRIMARY) {
-          tca = d[0] * s.x + d[1] * s.y + d[2] * s.z;
-          disc = tca * tca - s.w;
+          const uint32_t pix = node / (uint32_t)P.spp;
+          const uint32_t sub = node - pix * (uint32_t)P.spp;
+          const int lrow = P.band_l0 + (int)(pix / (uint32_t)W);
+          const int g = P.fr64.spp_grid;
+          double ray[3];
+          primary_ray<double>(P.fr64, (int)(pix % (uint32_t)W), P.rm.local_to_y(lrow), (int)(sub % g), (int)(sub / g), ray);
+          a[q][0] = -(float)ray[0]; a[q][1] = -(float)ray[1]; a[q][2] = -(float)ray[2];
         } else {
-          const float L0 = s.x - o[0], L1 = s.y - o[1], L2 = s.z - o[2];
-          tca = d[0] * L0 + d[1] * L1 + d[2] * L2;
-          const float d2 = (L0 * L0 + L1 * L1 + L2 * L2) - tca * tca;
-          disc = s.w - d2;
-          if (disc >= 0.f) {   // candidate: redo d2 as |L - tca d|^2, which does not cancel for r = 500
-            const float v0 = L0 - tca * d[0], v1 = L1 - tca * d[1], v2 = L2 - tca * d[2];
-            disc = s.w - (v0 * v0 + v1 * v1 + v2 * v2);
-          }
-        }
-        if (disc >= 0.f) {
-          const float thc = sqrtf(disc);
-          const float t0 = tca - thc, t1 = tca + thc;
-          const float t = (t0 >= eps) ? t0 : ((t1 >= eps) ? t1 : WF_INF);
-          if (t < best) { best = t; hit_i = j; flip = (t0 < eps); }
+          const float4 ro = P.b.ray_o[node], rd = P.b.ray_d[node];
+          a[q][0] = -ro.x; a[q][1] = -ro.y; a[q][2] = -ro.z;
+          b[q][0] = ro.w; b[q][1] = rd.x; b[q][2] = rd.y;
         }
       }
     }
+    if (PRIMARY) sweep_primary<R>(tab, P.primary_x, n_pad, a, active, best, eps);
+    else sweep_general<R>(tab, P.geom, n_pad, a, b, active, best, eps);
     __syncwarp();
-
-    // ---- hit record, directions, sampler, light terms --------------------------------------------
-    bool want_refl = false, want_refr = false;
-    float p[3] = {0.f, 0.f, 0.f}, rdir[3] = {0.f, 0.f, 0.f}, fdir[3] = {0.f, 0.f, 0.f};
-    float w_refl = 0.f, w_refr = 0.f;
-    int first_light = -1;
-    if (active) {
-      if (hit_i < 0) {                                    // main.js:231
-        P.b.pos[node] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
-        P.b.base[node] = make_float4(1.f, 0.f, 0.f, __int_as_float(0));
+#pragma unroll
+    for (int q = 0; q < R; q++) {
+      WfRay r;
+      r.node = (uint32_t)base + (uint32_t)q * 32u + lane;
+      r.active = active[q];
+      r.path = 1; r.pixsub = r.node; r.segs_left = P.fr64.segs;
+      if (PRIMARY) {
+        r.o[0] = P.origin[0]; r.o[1] = P.origin[1]; r.o[2] = P.origin[2];
+        r.d[0] = -a[q][0]; r.d[1] = -a[q][1]; r.d[2] = -a[q][2];
       } else {
-        const float4 g = __ldg(P.geom + hit_i);
-        const DevMaterial<float>& m = P.sc.mtl[hit_i];
-        p[0] = o[0] + d[0] * best; p[1] = o[1] + d[1] * best; p[2] = o[2] + d[2] * best;
-        float nn[3] = {p[0] - g.x, p[1] - g.y, p[2] - g.z};
-        const float nl = sqrtf(nn[0] * nn[0] + nn[1] * nn[1] + nn[2] * nn[2]);
-        if (nl != 0.f) { const float r = 1.f / nl; nn[0] *= r; nn[1] *= r; nn[2] *= r; }
-        const float l[3] = {flip ? -nn[0] : nn[0], flip ? -nn[1] : nn[1], flip ? -nn[2] : nn[2]};
-        const float a1 = m.albedo[1], a2 = m.albedo[2], a3 = m.albedo[3], a4 = m.albedo[4];
-        const float dn = d[0] * nn[0] + d[1] * nn[1] + d[2] * nn[2];
-        if (a3 > 0.f) {                                   // main.js:233-239
-          const float tt = -(2.f * dn);
-          rdir[0] = d[0] + nn[0] * tt; rdir[1] = d[1] + nn[1] * tt; rdir[2] = d[2] + nn[2] * tt;
-          const float len = sqrtf(rdir[0] * rdir[0] + rdir[1] * rdir[1] + rdir[2] * rdir[2]);
-          if (len != 0.f) {
-            const float r = 1.f / len; rdir[0] *= r; rdir[1] *= r; rdir[2] *= r;
-            want_refl = segs_left > 1;                    // a child with segs == 0 returns [0,0,0]
-            w_refl = a3;
-          }
+        r.o[0] = -a[q][0]; r.o[1] = -a[q][1]; r.o[2] = -a[q][2];
+        r.d[0] = b[q][0]; r.d[1] = b[q][1]; r.d[2] = b[q][2];
+        if (r.active) {
+          const int2 lk = P.b.link[r.node];
+          r.path = (uint32_t)lk.y & 0xffffffu;
+          r.segs_left = (int)((uint32_t)lk.y >> 24);
+          r.pixsub = __float_as_uint(P.b.ray_d[r.node].w);   // pixel*spp+sub of the level-1 ancestor
         }
-        if (a4 > 0.f) {                                   // main.js:241-266
-          float norm[3], eta;
-          float cosi = -js_max<float>(-1.f, js_min<float>(1.f, dn));
-          if (cosi < 0.f) { cosi = -cosi; norm[0] = -nn[0]; norm[1] = -nn[1]; norm[2] = -nn[2]; eta = m.refract_index; }
-          else { norm[0] = nn[0]; norm[1] = nn[1]; norm[2] = nn[2]; eta = 1.f / m.refract_index; }
-          const float k = 1.f - eta * eta * (1.f - cosi * cosi);
-          if (k > 0.f) {
-            const float q = eta * cosi - sqrtf(k);
-            fdir[0] = d[0] * eta + norm[0] * q; fdir[1] = d[1] * eta + norm[1] * q; fdir[2] = d[2] * eta + norm[2] * q;
-          } else {
-            const float tt = -(2.f * (d[0] * norm[0] + d[1] * norm[1] + d[2] * norm[2]));
-            fdir[0] = d[0] + norm[0] * tt; fdir[1] = d[1] + norm[1] * tt; fdir[2] = d[2] + norm[2] * tt;
-          }
-          const float len = sqrtf(fdir[0] * fdir[0] + fdir[1] * fdir[1] + fdir[2] * fdir[2]);
-          if (len != 0.f) {
-            const float r = 1.f / len; fdir[0] *= r; fdir[1] *= r; fdir[2] *= r;
-            want_refr = segs_left > 1;
-            w_refr = a4;
-          }
-        }
-        // sampler (main.js:320); u,v only matter to the texture sampler
-        float u = 0.f, v = 0.f, rgb[3];
-        if (m.sampler_kind == RTB_SAMPLER_TEXTURE) {
-          u = atan2f(-nn[2], -nn[0]) / 3.14159265358979323846f / 2.f + 0.5f;
-          v = asinf(-nn[1]) / (3.14159265358979323846f / 2.f) / 2.f + 0.5f;
-        }
-        run_sampler<float>(P.sc, m, nn, u, v, P.fr64.star_mode, P.fr64.star_seed, px, py, sub, path, rgb);
-        // occlusion-independent light terms (main.js:286-292, 306-313)
-        uint32_t mask = 0;
-        float q[RTB_MAX_LIGHTS] = {0.f, 0.f, 0.f, 0.f}, sp[RTB_MAX_LIGHTS] = {0.f, 0.f, 0.f, 0.f};
-        if (a1 > 0.f || a2 > 0.f) {
-          for (int k = 0; k < P.sc.n_lights; k++) {
-            float sv[3] = {P.sc.lights[k][0] - p[0], P.sc.lights[k][1] - p[1], P.sc.lights[k][2] - p[2]};
-            const float mag = sv[0] * sv[0] + sv[1] * sv[1] + sv[2] * sv[2];
-            const float len = sqrtf(mag);
-            if (len != 0.f) { const float r = 1.f / len; sv[0] *= r; sv[1] *= r; sv[2] *= r; }
-            const float sdot = sv[0] * l[0] + sv[1] * l[1] + sv[2] * l[2];
-            if (!(sdot > 0.f)) continue;
-            mask |= 1u << k;
-            q[k] = sdot / mag;
-            if (a2 > 0.f) {
-              // light_ref = normal3D(reflect3D(-sv, l)); spec_dot = dir . (-light_ref)
-              const float tt = 2.f * sdot;                 // -(2 * dot(-sv, l))
-              float lr[3] = {-sv[0] + l[0] * tt, -sv[1] + l[1] * tt, -sv[2] + l[2] * tt};
-              const float ll = sqrtf(lr[0] * lr[0] + lr[1] * lr[1] + lr[2] * lr[2]);
-              if (ll != 0.f) { const float r = 1.f / ll; lr[0] *= r; lr[1] *= r; lr[2] *= r; }
-              const float sd = -(d[0] * lr[0] + d[1] * lr[1] + d[2] * lr[2]);
-              if (sd > 0.f) sp[k] = powf(sd, m.specular_exponent);
-            }
-          }
-        }
-        if (mask) first_light = __ffs((int)mask) - 1;
-        P.b.pos[node] = make_float4(p[0], p[1], p[2], __int_as_float(hit_i));
-        P.b.base[node] = make_float4(rgb[0], rgb[1], rgb[2], __int_as_float((int)mask));
-        P.b.lq[node] = make_float4(q[0], sp[0], q[1], sp[1]);
-        if (P.b.lq2) P.b.lq2[node] = make_float4(q[2], sp[2], q[3], sp[3]);
-        P.b.acc[node] = make_float4(P.sc.light_intensity, 0.f, 0.f, 0.f);
       }
-      P.b.child_a[node] = make_float4(0.f, 0.f, 0.f, 0.f);
-      P.b.child_b[node] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-
-    // ---- warp-compacted child allocation (north star: ballot/shuffle compaction of live rays) -------
-    const uint32_t b1 = __ballot_sync(0xffffffffu, want_refl);
-    const uint32_t b2 = __ballot_sync(0xffffffffu, want_refr);
-    const uint32_t total = __popc(b1) + __popc(b2);
-    if (total) {
-      uint32_t cbase = 0;
-      if (lane == 0) cbase = atomicAdd(&P.b.ctr->node_count, total);
-      cbase = __shfl_sync(0xffffffffu, cbase, 0) + P.n_sub;
-      const uint32_t pixsub = PRIMARY ? node : __float_as_uint(P.b.ray_d[active ? node : begin].w);
-      if (want_refl) {
-        const uint32_t c = cbase + __popc(b1 & lanemask_lt());
-        if (c < P.b.cap_nodes) {
-          P.b.ray_o[c] = make_float4(p[0], p[1], p[2], rdir[0]);
-          P.b.ray_d[c] = make_float4(rdir[1], rdir[2], w_refl, __uint_as_float(pixsub));
-          P.b.link[c] = make_int2((int)node, (int)((2u * path) | ((uint32_t)(segs_left - 1) << 24)));
-        } else { P.b.ctr->overflow = 1u; P.sticky->overflow = 1u; }
-      }
-      if (want_refr) {
-        const uint32_t c = cbase + __popc(b1) + __popc(b2 & lanemask_lt());
-        if (c < P.b.cap_nodes) {
-          P.b.ray_o[c] = make_float4(p[0], p[1], p[2], fdir[0]);
-          P.b.ray_d[c] = make_float4(fdir[1], fdir[2], w_refr, __uint_as_float(pixsub));
-          P.b.link[c] = make_int2((int)node, (int)((2u * path + 1u) | ((uint32_t)(segs_left - 1) << 24)));
-        } else { P.b.ctr->overflow = 1u; P.sticky->overflow = 1u; }
-      }
-    }
-    // ---- warp-compacted shadow queue push: first light that faces the surface -----------------------
-    for (int k = 0; k < P.sc.n_lights; k++) {
-      const uint32_t bk = __ballot_sync(0xffffffffu, first_light == k);
-      if (!bk) continue;
-      uint32_t qb = 0;
-      if (lane == (uint32_t)(__ffs((int)bk) - 1)) qb = atomicAdd(&P.b.ctr->sq_count[k], (uint32_t)__popc(bk));
-      qb = __shfl_sync(0xffffffffu, qb, __ffs((int)bk) - 1);
-      if (first_light == k) P.b.sq[k][qb + __popc(bk & lanemask_lt())] = node;
+      process_hit(P, r, best[q], lane);
     }
   }
   // stats
@@ -305,87 +508,113 @@ wf_trace_kernel(const __grid_constant__ WfParams P, int level) {
 }
 
 // ---- SHADOW ---------------------------------------------------------------------------------------------
+// Occluder sweep of main.js:293-304 for light k, traced from the light toward hit.p.  Same fast test as
+// sweep_primary (table = C - light, sc); the slow path applies the reference's [0.001, light_len)
+// window along the reference's own ray (from hit.p toward the light): t = light_len - s.
 __global__ void __launch_bounds__(WF_THREADS)
 wf_shadow_kernel(const __grid_constant__ WfParams P, int k) {
+  constexpr int R = R_SHARED;
   extern __shared__ float4 tab[];
-  const int n = P.sc.n_spheres;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) tab[i] = P.light_tab[k][i];
+  const int n = P.sc.n_spheres, n_pad = P.n_pad;
+  for (int i = threadIdx.x; i < n_pad; i += blockDim.x) tab[i] = P.light_tab[k][i];
   __syncthreads();
+  const float4* __restrict__ exact = P.light_x[k];
   const uint32_t count = *((volatile uint32_t*)&P.b.ctr->sq_count[k]);
   const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
   const float eps = P.sc.eps;
   const float lx = P.sc.lights[k][0], ly = P.sc.lights[k][1], lz = P.sc.lights[k][2];
   unsigned long long my_rays = 0, my_tests = 0;
+  constexpr uint32_t CHUNK = 32u * R;
 
-  for (uint64_t base = (uint64_t)gwarp * 32u; base < count; base += (uint64_t)nwarps * 32u) {
-    const uint32_t e = (uint32_t)base + lane;
-    const bool active = e < count;
-    uint32_t node = 0;
-    int hit_i = -1;
-    float w[3] = {0.f, 0.f, 1.f}, len = 0.f, I = 0.f;
-    if (active) {
-      node = P.b.sq[k][e];
-      const float4 ps = P.b.pos[node];
-      hit_i = __float_as_int(ps.w);
-      // direction light -> p (= -shadow_vec) and light_len (main.js:287-290)
-      w[0] = ps.x - lx; w[1] = ps.y - ly; w[2] = ps.z - lz;
-      len = sqrtf(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
-      if (len != 0.f) { const float r = 1.f / len; w[0] *= r; w[1] *= r; w[2] *= r; }
-      I = P.b.acc[node].x;
-      my_rays++;
+  for (;;) {
+    const uint64_t base = (uint64_t)next_chunk(&P.b.ctr->work_shadow[k], lane) * CHUNK;
+    if (base >= count) break;
+    uint32_t node[R];
+    int hit_i[R];
+    float nw[R][3], len[R], I[R];      // nw = -(direction light -> p)
+    uint32_t mask[R];
+    bool active[R];
+#pragma unroll
+    for (int q = 0; q < R; q++) {
+      const uint32_t e = (uint32_t)base + (uint32_t)q * 32u + lane;
+      active[q] = e < count;
+      node[q] = 0; hit_i[q] = -1; len[q] = 0.f; I[q] = 0.f; mask[q] = 0;
+      nw[q][0] = nw[q][1] = nw[q][2] = 0.f;                // idle / dead slot: never a candidate
+      if (active[q]) {
+        node[q] = P.b.sq[k][e];
+        const float4 ps = P.b.pos[node[q]];
+        hit_i[q] = __float_as_int(ps.w);
+        // direction light -> p (= -shadow_vec) and light_len (main.js:287-290)
+        float wx = ps.x - lx, wy = ps.y - ly, wz = ps.z - lz;
+        len[q] = sqrtf(wx * wx + wy * wy + wz * wz);
+        if (len[q] != 0.f) { const float rr = 1.f / len[q]; wx *= rr; wy *= rr; wz *= rr; }
+        I[q] = P.b.acc[node[q]].x;
+        my_rays++;
+        if (I[q] != 0.f) { nw[q][0] = -wx; nw[q][1] = -wy; nw[q][2] = -wz; }
+      }
     }
-    bool live = active && I != 0.f;
-    for (int j0 = 0; j0 < n; j0 += 64) {                  // main.js:293-304, all lanes share the table
-      if (!__any_sync(0xffffffffu, live)) break;          // every lane already fully occluded
-      const int j1 = min(n, j0 + 64);
-      if (live) {
-        my_tests += (unsigned long long)(j1 - j0);
-#pragma unroll 4
-        for (int j = j0; j < j1; j++) {
-          const float4 s = tab[j];
-          const float tca = w[0] * s.x + w[1] * s.y + w[2] * s.z;
-          const float disc = tca * tca - s.w;
-          if (disc >= 0.f && j != hit_i) {
-            const float thc = sqrtf(disc);
-            // parameters along the reference's ray (from hit.p toward the light): t = len - s
-            const float t0 = len - (tca + thc), t1 = len - (tca - thc);
-            const float t = (t0 >= eps) ? t0 : ((t1 >= eps) ? t1 : WF_INF);
-            if (t < len) {
-              const float a4 = P.sc.mtl[j].albedo[4];
-              if (a4 != 0.f) I /= a4; else I = 0.f;      // main.js:298-302
-            }
+    for (int j = 0; j < n_pad; j += WF_GROUP) {
+      if ((j & 127) == 0) {                                 // all rays of the warp fully occluded?
+        bool l = false;
+#pragma unroll
+        for (int q = 0; q < R; q++) l |= (I[q] != 0.f);
+        if (!__any_sync(0xffffffffu, l)) break;
+#pragma unroll
+        for (int q = 0; q < R; q++) if (I[q] != 0.f) my_tests += (unsigned long long)min(128, n - j);
+      }
+#pragma unroll
+      for (int u = 0; u < WF_GROUP / 2; u++) {
+        const float4 A = tab[j + 2 * u], B = tab[j + 2 * u + 1];
+#pragma unroll
+        for (int q = 0; q < R; q++) {
+          float2 t = __ffma2_rn(f2(nw[q][2], nw[q][2]), f2(B.x, B.y), f2(B.z, B.w));
+          t = __ffma2_rn(f2(nw[q][1], nw[q][1]), f2(A.z, A.w), t);
+          t = __ffma2_rn(f2(nw[q][0], nw[q][0]), f2(A.x, A.y), t);
+          mask[q] = push_sign(push_sign(mask[q], t.x), t.y);
+        }
+      }
+      uint32_t any = 0;
+#pragma unroll
+      for (int q = 0; q < R; q++) any |= mask[q];
+      if (any & 0xffu) {
+#pragma unroll
+        for (int q = 0; q < R; q++) {
+          const uint32_t m = mask[q] & 0xffu;
+          if (m && I[q] != 0.f) {
+            I[q] = slow_shadow(exact, P.sc.mtl, j, m, nw[q][0], nw[q][1], nw[q][2], len[q], hit_i[q], eps, I[q]);
+            if (I[q] == 0.f) nw[q][0] = nw[q][1] = nw[q][2] = 0.f;   // fully occluded: stop testing
           }
         }
-        if (I == 0.f) live = false;
       }
     }
-    int next = -1;
-    if (active) {
-      float4 a = P.b.acc[node];
-      a.x = I;
-      const uint32_t mask = (uint32_t)__float_as_int(P.b.base[node].w);
-      if (I != 0.f) {                                     // main.js:305-313
-        const float4 lq = (k < 2) ? P.b.lq[node] : P.b.lq2[node];
-        const float qk = (k & 1) ? lq.z : lq.x, sk = (k & 1) ? lq.w : lq.y;
-        a.y += I * qk;
-        a.z += sk;
+#pragma unroll
+    for (int q = 0; q < R; q++) {
+      int next = -1;
+      if (active[q]) {
+        float4 a = P.b.acc[node[q]];
+        a.x = I[q];
+        const uint32_t lmask = (uint32_t)__float_as_int(P.b.base[node[q]].w);
+        if (I[q] != 0.f) {                                 // main.js:305-313
+          const float4 lq = (k < 2) ? P.b.lq[node[q]] : P.b.lq2[node[q]];
+          const float qk = (k & 1) ? lq.z : lq.x, sk = (k & 1) ? lq.w : lq.y;
+          a.y += I[q] * qk;
+          a.z += sk;
+        }
+        P.b.acc[node[q]] = a;
+        const uint32_t rest = lmask & ~((2u << k) - 1u);   // facing lights after k
+        if (I[q] != 0.f && rest) next = __ffs((int)rest) - 1;   // carry light_intensity to that light
       }
-      P.b.acc[node] = a;
-      const uint32_t rest = mask & ~((2u << k) - 1u);     // facing lights after k
-      if (I != 0.f && rest) next = __ffs((int)rest) - 1;  // carry light_intensity to that light
-    }
-    __syncwarp();
-    // warp-compacted hand-off; lanes may target different queues, so one ballot per later light
-    for (int k2 = k + 1; k2 < P.sc.n_lights; k2++) {
-      const uint32_t bk = __ballot_sync(0xffffffffu, next == k2);
-      if (!bk) continue;
-      const int leader = __ffs((int)bk) - 1;
-      uint32_t qb = 0;
-      if ((int)lane == leader) qb = atomicAdd(&P.b.ctr->sq_count[k2], (uint32_t)__popc(bk));
-      qb = __shfl_sync(0xffffffffu, qb, leader);
-      if (next == k2) P.b.sq[k2][qb + __popc(bk & lanemask_lt())] = node;
+      __syncwarp();
+      // warp-compacted hand-off; lanes may target different queues, so one ballot per later light
+      for (int k2 = k + 1; k2 < P.sc.n_lights; k2++) {
+        const uint32_t bk = __ballot_sync(0xffffffffu, next == k2);
+        if (!bk) continue;
+        const int leader = __ffs((int)bk) - 1;
+        uint32_t qb = 0;
+        if ((int)lane == leader) qb = atomicAdd(&P.b.ctr->sq_count[k2], (uint32_t)__popc(bk));
+        qb = __shfl_sync(0xffffffffu, qb, leader);
+        if (next == k2) P.b.sq[k2][qb + __popc(bk & lanemask_lt())] = node[q];
+      }
     }
   }
   for (int o2 = 16; o2 > 0; o2 >>= 1) {
@@ -516,12 +745,13 @@ void wf_free() {
 
 int wf_render(RtbScene_* s, const RtbCamera* cam, const DevFrameT<float>& fr32, const RowMap& rm,
               uint8_t* d_out, cudaStream_t st, RtbStats* stats, bool want_counts) {
-  (void)fr32; (void)want_counts;
+  (void)want_counts;
   const int W = cam->width;
   const int n_rows = rm.n_local();
   if (n_rows <= 0) return RTB_OK;
   const int n = s->n_spheres;
-  const size_t smem = (size_t)n * sizeof(float4);
+  const int n_pad = s->n_pad;
+  const size_t smem = (size_t)n_pad * sizeof(float4);
   if (smem > g_rtb.smem_optin) {
     rtb_set_error("wavefront kernels stage all %d spheres in shared memory (%zu B > %zu B available)",
                   n, smem, g_rtb.smem_optin);
@@ -532,17 +762,13 @@ int wf_render(RtbScene_* s, const RtbCamera* cam, const DevFrameT<float>& fr32, 
     return RTB_ERR_UNSUPPORTED;
   }
 
-  // primary table: per-sphere constants of rays leaving the camera origin, in fp64, rounded once
+  // primary tables: per-sphere constants of rays leaving the camera origin, in fp64, rounded once
   if (!s->primary_valid || s->primary_origin[0] != cam->origin[0] || s->primary_origin[1] != cam->origin[1] ||
       s->primary_origin[2] != cam->origin[2]) {
-    for (int i = 0; i < n; i++) {
-      const RtbSphere& sp = s->spheres[i];
-      const double L0 = sp.origin[0] - cam->origin[0], L1 = sp.origin[1] - cam->origin[1],
-                   L2 = sp.origin[2] - cam->origin[2];
-      s->h_primary_tab[i] = make_float4((float)L0, (float)L1, (float)L2,
-                                        (float)((L0 * L0 + L1 * L1 + L2 * L2) - sp.r2));
-    }
+    float4* h_x = s->h_primary_tab + n_pad;
+    wf_make_table(s->spheres.data(), n, n_pad, cam->origin, s->h_primary_tab, h_x);
     RTB_CUDA(cudaMemcpyAsync(s->d_primary_tab, s->h_primary_tab, smem, cudaMemcpyHostToDevice, st));
+    RTB_CUDA(cudaMemcpyAsync(s->d_primary_x, h_x, smem, cudaMemcpyHostToDevice, st));
     // the pinned staging buffer is rewritten by the next camera: wait for the copy
     RTB_CUDA(cudaStreamSynchronize(st));
     for (int c = 0; c < 3; c++) s->primary_origin[c] = cam->origin[c];
@@ -580,8 +806,11 @@ int wf_render(RtbScene_* s, const RtbCamera* cam, const DevFrameT<float>& fr32, 
   if (s->n_lights <= 2) P.b.lq2 = nullptr;                // kernels key the lights-2/3 store on this
   P.sticky = reinterpret_cast<WfSticky*>(reinterpret_cast<char*>(g_rtb.wf.ctr) + sizeof(WfCounters));
   P.geom = reinterpret_cast<const float4*>(s->d_geom32);
+  P.geom_tab = s->d_geom_tab;
   P.primary_tab = s->d_primary_tab;
-  for (int k = 0; k < s->n_lights; k++) P.light_tab[k] = s->d_light_tab[k];
+  P.primary_x = s->d_primary_x;
+  for (int k = 0; k < s->n_lights; k++) { P.light_tab[k] = s->d_light_tab[k]; P.light_x[k] = s->d_light_x[k]; }
+  P.n_pad = n_pad;
   P.spp = spp;
   P.aligned4 = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_out) & 15u) == 0);
 
