@@ -67,6 +67,9 @@ struct WfParams {
 };
 
 constexpr int WF_THREADS = 256;
+#ifndef WF_MIN_CTAS
+#define WF_MIN_CTAS 2
+#endif
 constexpr float WF_INF = __builtin_huge_valf();
 constexpr int WF_GROUP = 8;              // spheres per candidate check; the unrolled body (4 sphere pairs x R
                                          // rays) must stay well inside the ~6 KB L0 instruction cache
@@ -424,7 +427,7 @@ __device__ __noinline__ void process_hit(const WfParams& P, const WfRay& r, unsi
 
 // ---- TRACE ----------------------------------------------------------------------------------------------
 template <bool PRIMARY>
-__global__ void __launch_bounds__(WF_THREADS)
+__global__ void __launch_bounds__(WF_THREADS, WF_MIN_CTAS)
 wf_trace_kernel(const __grid_constant__ WfParams P, int level) {
   constexpr int R = PRIMARY ? R_SHARED : R_GENERAL;
   extern __shared__ float4 tab[];
@@ -511,7 +514,7 @@ wf_trace_kernel(const __grid_constant__ WfParams P, int level) {
 // Occluder sweep of main.js:293-304 for light k, traced from the light toward hit.p.  Same fast test as
 // sweep_primary (table = C - light, sc); the slow path applies the reference's [0.001, light_len)
 // window along the reference's own ray (from hit.p toward the light): t = light_len - s.
-__global__ void __launch_bounds__(WF_THREADS)
+__global__ void __launch_bounds__(WF_THREADS, WF_MIN_CTAS)
 wf_shadow_kernel(const __grid_constant__ WfParams P, int k) {
   constexpr int R = R_SHARED;
   extern __shared__ float4 tab[];

@@ -1,0 +1,296 @@
+"""CPU tests of the oracle (C float64 restatement of main.js) and of the reference-shaped host layer:
+hand-derived known answers from the reference source, JS number semantics, the
+independent literal Python port as second witness, and the committed golden frames produced by
+executing the unmodified main.js (tests/golden/, see oracle/gen_golden.py)."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+from conftest import lsb_stats
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+# ---- host-side inputs that fix results (main.js:85-105, 107-163) ---------------------------------------
+
+def test_default_camera_axes(rt):
+    """lookAt([0,1.5,10],[0,1.5,0],[0,1,0]) => axisX=(-1,0,0) axisY=(0,1,0) axisZ=(0,0,-1) (main.js:90-100)."""
+    cam = rt.scenes.demo_camera(1280, 720)
+    assert cam.origin == [0, 1.5, 10]
+    assert cam.axisX == [-1.0, 0.0, 0.0] and cam.axisY == [0.0, 1.0, 0.0] and cam.axisZ == [0.0, 0.0, -1.0]
+    assert cam.projW == 640 and cam.projH == 360
+    assert cam.projD == 640 / math.tan((60 * math.pi / 180) / 2)      # main.js:102-105
+
+
+def test_demo_sort_order(rt):
+    """objects.sort by surface_area / distance (main.js:159-163); ties keep insertion order."""
+    objs = rt.scenes.demo_objects()
+    centres = [tuple(o.origin) for o in objs]
+    assert centres == [
+        (1.0, 0.25, 3.0), (0.0, 0.25, 3.0), (0.0, 2.5, -2.0), (1.5, 2.5, 0.0), (-1.5, 2.5, 0.0),
+        (-50.0, 20.0, -100.0), (-2.5, 0.5, 3.0), (2.5, 0.5, 3.0), (0.0, 1.0, -2.0), (-1.5, 1.0, 0.0),
+        (1.5, 1.0, 0.0), (50.0, 20.0, -100.0), (0.0, -500.0, 0.0), (0.0, 0.0, 0.0)]
+    kinds = [o.mtl.sampler.kind for o in objs]
+    A = rt._abi
+    assert kinds[1] == A.RTB_SAMPLER_TEXTURE and kinds[5] == A.RTB_SAMPLER_TEXTURE and kinds[11] == A.RTB_SAMPLER_TEXTURE
+    assert kinds[12] == A.RTB_SAMPLER_CHECKER and kinds[13] == A.RTB_SAMPLER_STARS
+    # createSphere stores r*r, not r (main.js:412-413)
+    assert objs[12].r2 == 250000.0 and objs[13].r2 == 25000000.0 and objs[0].r2 == 0.0625
+
+
+def test_checker_texture_and_planet_assets(rt):
+    t = rt.createTexture()
+    rt.checkerTexture(t, 16, 8, [0, 0, 0], [1, 1, 1])       # main.js:153-154, 353-373
+    px = t.texels.reshape(8, 16, 4)
+    for y in range(8):
+        for x in range(16):
+            want = 255 if ((x & 1) ^ (y & 1)) else 0
+            assert tuple(px[y, x]) == (want, want, want, 255)
+    earth, mars = rt.scenes.load_planet_textures()
+    assert (earth.width, earth.height) == (256, 128) and (mars.width, mars.height) == (256, 128)
+    assert earth.texels.reshape(-1, 4)[:, 3].min() == 255     # opaque palette PNGs
+
+
+def test_png_decoder_roundtrip(rt, tmp_path):
+    """loadTexture's PNG path: palette / RGB / RGBA, every filter type, against zlib-built files."""
+    import struct
+    import zlib
+
+    png = rt.png
+
+    def chunk(t, b):
+        return struct.pack(">I", len(b)) + t + b + struct.pack(">I", zlib.crc32(t + b) & 0xffffffff)
+
+    rng = np.random.default_rng(3)
+    w, h = 7, 5
+    img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    raw = bytearray()
+    prev = np.zeros(w * 3, np.int32)
+    for y in range(h):                                        # cycle through filter types 0..4
+        line = img[y].reshape(-1).astype(np.int32)
+        ft = y % 5
+        out = np.zeros_like(line)
+        for i in range(len(line)):
+            a = line[i - 3] if i >= 3 else 0
+            b = prev[i]
+            c = prev[i - 3] if i >= 3 else 0
+            if ft == 0: p = 0
+            elif ft == 1: p = a
+            elif ft == 2: p = b
+            elif ft == 3: p = (a + b) >> 1
+            else:
+                pa, pb, pc = abs(b - c), abs(a - c), abs(a + b - 2 * c)
+                p = a if (pa <= pb and pa <= pc) else (b if pb <= pc else c)
+            out[i] = (line[i] - p) & 255
+        raw += bytes([ft]) + bytes(out.astype(np.uint8))
+        prev = line
+    data = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 2, 0, 0, 0)) + \
+        chunk(b"IDAT", zlib.compress(bytes(raw))) + chunk(b"IEND", b"")
+    ww, hh, rgba = png.decode_rgba8(data)
+    assert (ww, hh) == (w, h) and np.array_equal(rgba[..., :3], img) and (rgba[..., 3] == 255).all()
+    # palette + tRNS
+    pal = rng.integers(0, 256, (4, 3), dtype=np.uint8)
+    idx = rng.integers(0, 4, (h, w), dtype=np.uint8)
+    raw = b"".join(b"\x00" + bytes(idx[y]) for y in range(h))
+    data = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 3, 0, 0, 0)) + \
+        chunk(b"PLTE", pal.tobytes()) + chunk(b"tRNS", bytes([0, 128])) + \
+        chunk(b"IDAT", zlib.compress(raw)) + chunk(b"IEND", b"")
+    _, _, rgba = png.decode_rgba8(data)
+    assert np.array_equal(rgba[..., :3], pal[idx])
+    assert np.array_equal(rgba[..., 3], np.array([0, 128, 255, 255], np.uint8)[idx])
+    t = rt.createTexture()
+    f = tmp_path / "t.png"
+    f.write_bytes(data)
+    rt.loadTexture(t, str(f))
+    assert t.loaded and (t.width, t.height) == (w, h)
+
+
+# ---- JS number semantics the restatement depends on --------------------------------------------------------
+
+def test_uint8_clamped_store(oracle):
+    """Uint8ClampedArray: NaN -> 0, clamp, round HALF TO EVEN (main.js:195-198)."""
+    L = oracle.lib()
+    cases = {float("nan"): 0, -3.0: 0, 0.49: 0, 0.5: 0, 0.51: 1, 1.5: 2, 2.5: 2, 3.5: 4, 254.5: 254,
+             254.51: 255, 255.0: 255, 300.0: 255, float("inf"): 255, -float("inf"): 0, 127.5: 128, 126.5: 126}
+    for v, want in cases.items():
+        assert L.oracle_clamped_u8(v) == want, v
+
+
+def test_toint32(oracle):
+    """`&` operand conversion (main.js:129-130)."""
+    L = oracle.lib()
+    for v, want in {0.9: 0, 1.0: 1, 1249.9999: 1249, -1.5: -1, 4294967296.0 + 5: 5, 2147483648.0: -2147483648,
+                    float("nan"): 0, float("inf"): 0}.items():
+        assert L.oracle_toint32(v) == want, v
+
+
+def test_sample_texture_addressing(rt, oracle):
+    """sampleTexture uses ceil(u*w)-1, clamped at 0 (main.js:343-351): u=0 -> x=0, u=1 -> x=w-1, and an
+    integer u*w selects the texel to the LEFT (differs from floor addressing)."""
+    import ctypes as C
+    A = rt._abi
+    w, h = 8, 4
+    tex = np.zeros((h, w, 4), np.uint8)
+    tex[..., 0] = np.arange(w)[None, :] * 10
+    tex[..., 1] = np.arange(h)[:, None] * 20
+    t = A.RtbTexture(w, h, tex.ctypes.data_as(C.POINTER(C.c_uint8)))
+    L = oracle.lib()
+
+    def s(u, v):
+        out = A.D3()
+        L.oracle_sample_texture(C.byref(t), u, v, out)
+        return round(out[0] * 255 / 10), round(out[1] * 255 / 20)
+
+    assert s(0.0, 0.0) == (0, 0)
+    assert s(1.0, 1.0) == (w - 1, h - 1)
+    assert s(0.5, 0.5) == (3, 1)          # u*w = 4 exactly -> ceil(4)-1 = 3, not floor(4) = 4
+    assert s(0.5 + 1e-9, 0.5 + 1e-9) == (4, 2)
+    assert s(1e-12, 1e-12) == (0, 0)
+
+
+# ---- intersectSphere / intersectWorld known answers -------------------------------------------------------
+
+def _one_sphere(rt, centre, r, albedo=(1, 0, 0, 0, 0), color=(0.25, 0.5, 0.75)):
+    return rt.SceneDesc([rt.createSphere(centre, r, rt.createMaterial(list(color), list(albedo), 10, 1.0))])
+
+
+def test_intersect_sphere_known_answers(rt, oracle):
+    """main.js:420-451 by hand: unit sphere at z=-5 seen from the origin along -z."""
+    sd = _one_sphere(rt, [0, 0, -5], 1)
+    t, e = oracle.intersect_sphere(sd, 0, [0, 0, 0], [0, 0, -1])
+    assert t == 4.0
+    assert e[1:4] == [0, 0, -4] and e[4:7] == [0, 0, 1] and e[7:10] == [0, 0, 1]      # p, n, l = n (outside)
+    # u = atan2(-n.z, -n.x)/pi/2 + 0.5 = atan2(-1, -0)/(2 pi) + 0.5 ; v = asin(-n.y)/(pi/2)/2 + 0.5 = 0.5
+    assert e[10] == math.atan2(-1.0, -0.0) / math.pi / 2 + 0.5 and e[11] == 0.5
+    # from inside: t0 < 0.001 -> t1 chosen and l = -n (main.js:430-432, 445)
+    t, e = oracle.intersect_sphere(sd, 0, [0, 0, -5], [0, 0, -1])
+    assert t == 1.0 and e[4:7] == [0, 0, -1] and e[7:10] == [0, 0, 1]
+    # miss, behind, and the 0.001 window
+    assert oracle.intersect_sphere(sd, 0, [0, 2, 0], [0, 0, -1], ext=False)[0] == math.inf
+    assert oracle.intersect_sphere(sd, 0, [0, 0, -10], [0, 0, -1], ext=False)[0] == math.inf
+    assert oracle.intersect_sphere(sd, 0, [0, 0, -4.0005], [0, 0, 1], ext=False)[0] == math.inf  # t1 = 0.0005 < eps
+    assert oracle.intersect_sphere(sd, 0, [0, 0, -4.002], [0, 0, 1], ext=False)[0] == pytest.approx(0.002, abs=1e-12)
+
+
+def test_intersect_world_known_answers(rt, oracle):
+    # no object hit -> [1,0,0] (main.js:231); segs == 0 -> [0,0,0] (main.js:221)
+    sd = _one_sphere(rt, [0, 0, -5], 1)
+    assert oracle.trace_ray(sd, 8, [0, 0, 0], [0, 1, 0])[0] == [1, 0, 0]
+    assert oracle.trace_ray(sd, 0, [0, 0, 0], [0, 0, -1])[0] == [0, 0, 0]
+    # pure ambient material: colour * albedo[0], no light loop (main.js:282, 322, 333)
+    rgb, cnt = oracle.trace_ray(sd, 8, [0, 0, 0], [0, 0, -1])
+    assert rgb == [0.25, 0.5, 0.75] and cnt["nodes"] == 1 and cnt["shadow_rays"] == 0 and cnt["sphere_tests"] == 1
+    # pure diffuse, one unoccluded light straight behind the camera: intensity 50 * dot / |sv|^2, clamped to 1
+    sd = rt.SceneDesc([rt.createSphere([0, 0, -5], 1, rt.createMaterial([1, 1, 1], [0, 1, 0, 0, 0], 10, 1.0))],
+                      lights=[[0, 0, 6]], light_intensity=50.0)
+    rgb, cnt = oracle.trace_ray(sd, 8, [0, 0, 0], [0, 0, -1])
+    assert rgb == [0.5, 0.5, 0.5]          # 50 * 1 / 100
+    assert cnt["shadow_rays"] == 1 and cnt["sphere_tests"] == 1     # occluder loop skips hit_i (main.js:294)
+
+
+def test_light_intensity_carries_across_lights(rt, oracle):
+    """main.js:284 declares light_intensity once OUTSIDE the light loop: an opaque
+    occluder on light 0 blacks out light 1 as well; a refractive one divides by albedo[4] and the
+    amplified value carries over."""
+    M, S = rt.createMaterial, rt.createSphere
+    floor = S([0, 0, -5], 1, M([1, 1, 1], [0, 1, 0, 0, 0], 10, 1.0))
+    lights = [[0, 10, -5 + 1e-9], [0, 0, 6]]     # light 0 above (grazing, facing by a hair), light 1 behind camera
+    # hit point is (0,0,-4); light 0 direction ~ (0,1,~0): shadow_dot > 0 only marginally
+    blocker_opaque = S([0, 5, -4.5], 0.4, M([1, 1, 1], [1, 0, 0, 0, 0], 10, 1.0))
+    blocker_glass = S([0, 5, -4.5], 0.4, M([1, 1, 1], [1, 0, 0, 0, 0.8], 10, 1.0))
+    lights = [[0, 10, -3], [0, 0, 6]]
+    base = oracle.trace_ray(rt.SceneDesc([floor], lights=lights), 8, [0, 0, 0], [0, 0, -1])[0][0]
+    # place the blocker on the segment hit(0,0,-4) -> light0(0,10,-3)
+    mid = [0, 5, -3.5]
+    for b, expect in ((S(mid, 0.4, blocker_opaque.mtl), "dark"), (S(mid, 0.4, blocker_glass.mtl), "bright")):
+        v = oracle.trace_ray(rt.SceneDesc([floor, b], lights=lights), 8, [0, 0, 0], [0, 0, -1])[0][0]
+        if expect == "dark":
+            assert v == 0.0                      # light 1 unobstructed, yet contributes nothing
+        else:
+            assert v > base                      # 50/0.8 carried into light 1 as well
+
+
+def test_demo_counters_match_survey(rt, oracle):
+    """SURVEY.md §3 cost-shape table (320x180, segs 8): 1.560 nodes/px, 1.423 shadow rays/px."""
+    sd = rt.SceneDesc(rt.scenes.demo_objects())
+    img, cnt = oracle.render(sd, rt.scenes.demo_camera(320, 180), rt.make_opts(segs=8))
+    px = 320 * 180
+    assert cnt["nodes"] / px == pytest.approx(1.560, abs=0.002)
+    assert cnt["shadow_rays"] / px == pytest.approx(1.423, abs=0.002)
+    assert cnt["sphere_tests"] / cnt["rays"] == pytest.approx(13.3, abs=0.1)
+    assert cnt["tir"] == 0                                            # TIR never fires in the demo
+    assert (img[..., 3] == 255).all()
+    _, cnt5 = oracle.render(sd, rt.scenes.demo_camera(320, 180), rt.make_opts(segs=5))
+    assert cnt5["nodes"] / px == pytest.approx(1.411, abs=0.002)
+
+
+def test_oracle_is_deterministic_across_threads_and_partitions(rt, oracle):
+    sd = rt.SceneDesc(rt.scenes.synth_objects(64, 5))
+    cam = rt.scenes.demo_camera(96, 54)
+    a, ca = oracle.render(sd, cam, rt.make_opts(segs=6), threads=1)
+    b, cb = oracle.render(sd, cam, rt.make_opts(segs=6), threads=0)
+    assert np.array_equal(a, b) and ca == cb
+    # stripes and row ranges partition the same frame
+    asm = np.zeros_like(a)
+    for r in range(3):
+        oracle.render(sd, cam, rt.make_opts(segs=6, stripe_rows=4, stripe_rank=r, stripe_world=3), out=asm)
+    assert np.array_equal(asm, a)
+    part = np.zeros_like(a)
+    oracle.render(sd, cam, rt.make_opts(segs=6, y0=10, y1=20), out=part)
+    assert np.array_equal(part[10:20], a[10:20]) and not part[:10].any() and not part[20:].any()
+    # spp_grid = 1 through the generalised sub-sample formula is the reference pixel centre
+    g1, _ = oracle.render(sd, cam, rt.make_opts(segs=6, spp_grid=1))
+    assert np.array_equal(g1, a)
+
+
+def test_camera_basis_frame0_equals_reference_camera(rt, oracle):
+    sd = rt.SceneDesc(rt.scenes.demo_objects())
+    ref, _ = oracle.render(sd, rt.scenes.demo_camera(80, 45), rt.make_opts(segs=4))
+    orbit0 = rt.scenes.orbit_cameras(80, 45, nframes=4)[0]
+    img, _ = oracle.render(sd, orbit0, rt.make_opts(segs=4))
+    assert np.array_equal(img, ref)
+
+
+def test_c3_counters_fixture_is_consistent(rt, oracle):
+    """The committed C3 counters (bench.py's ray / flop denominators) against a fresh oracle run on a
+    subset of rows of the same scene."""
+    c = json.load(open(os.path.join(GOLDEN, "counters_c3_synth1024_4k.json")))
+    assert c["width"] == 3840 and c["height"] == 2160 and c["n_spheres"] == 1024 and c["segs"] == 8
+    assert c["rays"] == c["nodes"] + c["shadow_rays"]
+    sd = rt.SceneDesc(rt.scenes.synth_objects(1024, 1024))
+    _, part = oracle.render(sd, rt.scenes.demo_camera(3840, 2160), rt.make_opts(segs=8), row_step=270)
+    rows = len(range(0, 2160, 270))
+    # 8 rows of 2160: the per-row average of the sample lies within a factor of the frame average
+    assert 0.4 < (part["rays"] / rows) / (c["rays"] / 2160) < 2.5
+
+
+# ---- second witness: literal Python transliteration ---------------------------------------------------------
+
+def test_python_port_matches_c_oracle_bytes(rt, oracle):
+    from oracle import pyoracle
+    sd = rt.SceneDesc(rt.scenes.demo_objects())
+    cam = rt.scenes.demo_camera(48, 27)
+    ref, _ = oracle.render(sd, cam, rt.make_opts(segs=8))
+    img = pyoracle.render(rt.scenes.demo_objects(), cam, segs=8)
+    assert np.array_equal(img, ref)
+
+
+# ---- golden frames from the unmodified main.js --------------------------------------------------------------
+
+def test_oracle_matches_main_js_golden(rt, oracle):
+    """tests/golden/mainjs_demo_*.npz: framebuffer of the UNMODIFIED /root/reference/main.js executed
+    under oracle/minijs (gen_golden.py).  The C restatement must reproduce it (+-1 LSB allowance for
+    libm vs the interpreter's Math, none expected)."""
+    files = sorted(f for f in os.listdir(GOLDEN) if f.startswith("mainjs_demo_") and f.endswith(".npz"))
+    assert files, "golden frames missing: run oracle/gen_golden.py in the build container"
+    sd = rt.SceneDesc(rt.scenes.demo_objects())
+    for f in files:
+        z = np.load(os.path.join(GOLDEN, f))
+        gold = z["rgba"]
+        h, w = gold.shape[:2]
+        img, _ = oracle.render(sd, rt.scenes.demo_camera(w, h), rt.make_opts(segs=8))
+        s = lsb_stats(img, gold)
+        assert s["within1"] == 1.0 and s["exact"] >= 0.9999, (f, s)
