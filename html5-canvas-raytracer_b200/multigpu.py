@@ -99,7 +99,8 @@ class StripedRenderer:
             return self.frame
         o = make_opts(stripe_rows=self.S, stripe_rank=self.rank, stripe_world=self.world, out_packed=1, **kw)
         self.r.redraw_device(camera, o, self.local.data_ptr(), stream, stats)
-        dist.all_gather_into_tensor(self.gathered, self.local)
+        # concatenated-along-dim-0 view: the form both NCCL and gloo accept
+        dist.all_gather_into_tensor(self.gathered.view(-1, self.W, 4), self.local)
         A.check(self.lib.rtb_unstripe_device(self.gathered.data_ptr(), self.frame.data_ptr(), self.W, self.H,
                                              self.S, self.world, stream))
         return self.frame
@@ -129,5 +130,5 @@ class FrameBatchRenderer:
         if self.world <= 1:
             self.step[0].copy_(self.mine)
         else:
-            dist.all_gather_into_tensor(self.step, self.mine)
+            dist.all_gather_into_tensor(self.step.view(-1, self.W, 4), self.mine)
         return self.step

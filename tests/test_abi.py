@@ -1,0 +1,138 @@
+"""The drop-in boundary without a GPU: the built C-ABI library loads, exports every symbol that
+include/rtb200.h declares, its struct layouts equal the ctypes mirror, the pure-host entry points
+behave, and computing entry points fail loudly (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "rtb200.h")
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.fixture(scope="module")
+def lib(rt):
+    if not os.path.exists(rt._abi.LIB_PATH):
+        builder = __import__("importlib").import_module("html5-canvas-raytracer_b200.build")
+        builder.build_library()
+    return rt._abi.load()
+
+
+def test_every_declared_symbol_is_exported(rt, lib):
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(rtb_[a-z0-9_]+)\s*\(", src)))
+    assert declared and sorted(rt._abi.EXPORTS) == declared
+    out = subprocess.run(["nm", "-D", "--defined-only", rt._abi.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (rtb_[a-z0-9_]+)", out))
+    assert set(declared) <= exported, set(declared) - exported
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.rtb_abi_version() == rt._abi.RTB_ABI_VERSION
+    assert b"sm_100a" in lib.rtb_version()
+
+
+def test_struct_layout_matches_header(rt, tmp_path):
+    """sizeof/offsetof from a C compile of the public header vs the ctypes mirror."""
+    A = rt._abi
+    structs = {"RtbMaterial": A.RtbMaterial, "RtbSphere": A.RtbSphere, "RtbTexture": A.RtbTexture,
+               "RtbSceneDesc": A.RtbSceneDesc, "RtbCamera": A.RtbCamera, "RtbRenderOpts": A.RtbRenderOpts,
+               "RtbStats": A.RtbStats}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void){"]
+    for name, st in structs.items():
+        lines.append(f'printf("{name} %zu\\n", sizeof({name}));')
+        for f, _ in st._fields_:
+            lines.append(f'printf("{name}.{f} %zu\\n", offsetof({name}, {f}));')
+    lines.append("return 0;}")
+    c = tmp_path / "layout.c"
+    c.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    subprocess.run([cc, "-std=c11", str(c), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout
+    got = dict(l.split() for l in out.strip().splitlines())
+    for name, st in structs.items():
+        assert int(got[name]) == C.sizeof(st), name
+        for f, _ in st._fields_:
+            assert int(got[f"{name}.{f}"]) == getattr(st, f).offset, f"{name}.{f}"
+
+
+def test_stripe_arithmetic_matches_python_twin(rt, lib):
+    mg = __import__("importlib").import_module("html5-canvas-raytracer_b200.multigpu")
+    for H in (1, 7, 16, 70, 150, 1080, 2160):
+        for S in (1, 4, 16):
+            for world in (1, 2, 3, 4, 8):
+                tot = 0
+                for r in range(world):
+                    n = lib.rtb_stripe_local_rows(H, S, r, world)
+                    assert n == len(mg.stripe_rows_of(H, S, r, world))
+                    tot += n
+                assert tot == H
+                assert lib.rtb_stripe_padded_rows(H, S, world) == mg.padded_rows(H, S, world)
+
+
+def test_default_opts_are_the_reference_literals(rt, lib):
+    o = rt._abi.RtbRenderOpts()
+    lib.rtb_default_opts(C.byref(o))
+    assert (o.segs, o.spp_grid, o.precision, o.kernel, o.star_mode) == (8, 1, rt.RTB_PRECISION_FP32, rt.RTB_KERNEL_AUTO, rt.RTB_STARS_OFF)
+    assert (o.y0, o.y1, o.stripe_world, o.out_packed) == (0, 0, 0, 0)
+
+
+def test_scene_flattening(rt):
+    objs = rt.scenes.demo_objects()
+    d = rt.SceneDesc(objs)
+    assert d.c.n_spheres == 14 and d.c.n_textures == 3 and d.c.n_lights == 2
+    assert list(d.c.lights[0]) == [5.0, 10.0, 5.0] and list(d.c.lights[1]) == [5.0, 10.0, 0.0]
+    assert d.c.light_intensity == 50.0 and d.c.eps == 0.001
+    home = d.c.spheres[12]
+    assert home.mtl.sampler_kind == rt._abi.RTB_SAMPLER_CHECKER
+    assert list(home.mtl.checker_freq) == [5000.0, 2500.0]
+    assert [list(c) for c in home.mtl.checker_color] == [[1, 1, 0], [1, 0, 1]]
+    sky = d.c.spheres[13]
+    assert (sky.mtl.star_threshold, sky.mtl.star_gain) == (0.001, 1000.0)
+    units = {d.c.spheres[i].mtl.texture_unit for i in (1, 5, 11)}
+    assert units == {0, 1, 2}
+    with pytest.raises(ValueError):
+        rt.createMaterial([1, 1], [0] * 5, 1, 1)
+    t = rt.createTexture()
+    m = rt.createMaterial([1, 1, 1], [1, 0, 0, 0, 0], 0, 1)
+    m.sampler = rt.textureSampler(t)
+    with pytest.raises(ValueError):                       # texture never loaded (main.js:167-178 would poll forever)
+        rt.SceneDesc([rt.createSphere([0, 0, 0], 1, m)])
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU behaviour")
+def test_no_gpu_means_loud_failure_not_fallback(rt, lib):
+    assert lib.rtb_init(-1) == rt._abi.RTB_ERR_NO_DEVICE
+    assert b"no CPU fallback" in lib.rtb_last_error()
+    with pytest.raises(rt.RtbError) as e:
+        rt.Renderer(rt.scenes.demo_objects())
+    assert e.value.code == rt._abi.RTB_ERR_NO_DEVICE
+    # nothing initialised: computing entry points refuse
+    h = C.c_void_p()
+    d = rt.SceneDesc(rt.scenes.demo_objects())
+    assert lib.rtb_scene_create(C.byref(d.c), C.byref(h)) == rt._abi.RTB_ERR_NOT_INIT
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is a checker: nothing under the product package (or its C sources) may reference it."""
+    pkg = os.path.join(ROOT, "html5-canvas-raytracer_b200")
+    for dp, _, files in os.walk(pkg):
+        if "_obj" in dp:
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".inl", ".cc")):
+                txt = open(os.path.join(dp, f), errors="replace").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
+                assert "liboracle" not in txt and "rt_oracle" not in txt, f
