@@ -184,6 +184,8 @@ def main():
     mg = importlib.import_module("html5-canvas-raytracer_b200.multigpu")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the render path has no CPU fallback")
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"       # keep NCCL's version banner off stdout: ONE JSON line
     rank, local_rank, world = mg.init_distributed()
     torch.cuda.set_device(local_rank)
     dist = torch.distributed if world > 1 else None
@@ -269,6 +271,8 @@ def main():
 
     if rank != 0:
         renderer.close()
+        dist.barrier()
+        dist.destroy_process_group()
         return
 
     # ---- roofline (FP32 compute) ------------------------------------------------------------------
@@ -335,6 +339,9 @@ def main():
                                 "sample": ci["sample"]}
     renderer.close()
     print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -1,0 +1,288 @@
+// napi_shim.cc — thin Node-API addon over the C ABI of include/rtb200.h.
+//
+//   const rtb = require('./rtb200.node');
+//   rtb.render(scene, camera, opts, colorbuf.data);      // fills the Uint8ClampedArray in place
+//
+// It replaces the pixel loops of main.js's redraw()/spanish() (main.js:180-199): JavaScript hands over
+// the same scene description main() builds (main.js:85-163) and gets back the bytes it would have
+// passed to putImageData (main.js:200).  See INTEGRATION.md for the patch to main.js.
+//
+// HEADER-FREE: this image has neither Node nor node_api.h, so the handful of Node-API prototypes used
+// here are declared below from the ABI-stable Node-API (C linkage, napi_status return, napi_ok == 0).
+// The napi_* symbols stay undefined in the .node file and are bound by the `node` executable when it
+// dlopen()s the addon.  NOT EXECUTED in this container (no Node); verify against a real node_api.h on
+// first contact with a Node install.
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "rtb200.h"
+
+extern "C" {
+typedef struct napi_env__* napi_env;
+typedef struct napi_value__* napi_value;
+typedef struct napi_callback_info__* napi_callback_info;
+typedef enum { napi_ok = 0 } napi_status;
+typedef napi_value (*napi_callback)(napi_env, napi_callback_info);
+typedef enum {
+  napi_int8_array, napi_uint8_array, napi_uint8_clamped_array, napi_int16_array, napi_uint16_array,
+  napi_int32_array, napi_uint32_array, napi_float32_array, napi_float64_array, napi_bigint64_array,
+  napi_biguint64_array
+} napi_typedarray_type;
+typedef enum {
+  napi_undefined, napi_null, napi_boolean, napi_number, napi_string, napi_symbol, napi_object,
+  napi_function, napi_external, napi_bigint
+} napi_valuetype;
+
+napi_status napi_get_cb_info(napi_env, napi_callback_info, size_t* argc, napi_value* argv, napi_value* this_arg, void** data);
+napi_status napi_get_named_property(napi_env, napi_value object, const char* utf8name, napi_value* result);
+napi_status napi_has_named_property(napi_env, napi_value object, const char* utf8name, bool* result);
+napi_status napi_get_array_length(napi_env, napi_value value, uint32_t* result);
+napi_status napi_get_element(napi_env, napi_value object, uint32_t index, napi_value* result);
+napi_status napi_get_value_double(napi_env, napi_value value, double* result);
+napi_status napi_get_value_int32(napi_env, napi_value value, int32_t* result);
+napi_status napi_typeof(napi_env, napi_value value, napi_valuetype* result);
+napi_status napi_is_typedarray(napi_env, napi_value value, bool* result);
+napi_status napi_is_array(napi_env, napi_value value, bool* result);
+napi_status napi_get_typedarray_info(napi_env, napi_value typedarray, napi_typedarray_type* type, size_t* length,
+                                     void** data, napi_value* arraybuffer, size_t* byte_offset);
+napi_status napi_create_function(napi_env, const char* utf8name, size_t length, napi_callback cb, void* data, napi_value* result);
+napi_status napi_set_named_property(napi_env, napi_value object, const char* utf8name, napi_value value);
+napi_status napi_create_object(napi_env, napi_value* result);
+napi_status napi_create_double(napi_env, double value, napi_value* result);
+napi_status napi_create_string_utf8(napi_env, const char* str, size_t length, napi_value* result);
+napi_status napi_get_undefined(napi_env, napi_value* result);
+napi_status napi_throw_error(napi_env, const char* code, const char* msg);
+}
+#define NAPI_AUTO_LENGTH SIZE_MAX
+
+namespace {
+
+struct Fail { std::string msg; };
+#define NAPI_OK(call) do { if ((call) != napi_ok) throw Fail{std::string("Node-API call failed: ") + #call}; } while (0)
+
+bool has(napi_env env, napi_value o, const char* k) {
+  bool r = false;
+  if (napi_has_named_property(env, o, k, &r) != napi_ok) return false;
+  if (!r) return false;
+  napi_value v; napi_valuetype t;
+  NAPI_OK(napi_get_named_property(env, o, k, &v));
+  NAPI_OK(napi_typeof(env, v, &t));
+  return t != napi_undefined && t != napi_null;
+}
+napi_value prop(napi_env env, napi_value o, const char* k) {
+  napi_value v;
+  NAPI_OK(napi_get_named_property(env, o, k, &v));
+  return v;
+}
+double num(napi_env env, napi_value v) {
+  double d = 0;
+  if (napi_get_value_double(env, v, &d) != napi_ok) throw Fail{"expected a number"};
+  return d;
+}
+double num_prop(napi_env env, napi_value o, const char* k, double dflt, bool required = false) {
+  if (!has(env, o, k)) {
+    if (required) throw Fail{std::string("missing property '") + k + "'"};
+    return dflt;
+  }
+  return num(env, prop(env, o, k));
+}
+void vec(napi_env env, napi_value o, const char* k, double* out, uint32_t n) {
+  if (!has(env, o, k)) throw Fail{std::string("missing property '") + k + "'"};
+  napi_value a = prop(env, o, k);
+  uint32_t len = 0;
+  NAPI_OK(napi_get_array_length(env, a, &len));
+  if (len < n) throw Fail{std::string("property '") + k + "' is too short"};
+  for (uint32_t i = 0; i < n; i++) {
+    napi_value e;
+    NAPI_OK(napi_get_element(env, a, i, &e));
+    out[i] = num(env, e);
+  }
+}
+
+// texels: Uint8ClampedArray / Uint8Array (loadTexture, main.js:391) or a plain Array of numbers
+// (checkerTexture writes 255*colour into `texels: []`, main.js:340, 358-366).
+void read_texels(napi_env env, napi_value t, size_t want, std::vector<uint8_t>& out) {
+  bool typed = false;
+  NAPI_OK(napi_is_typedarray(env, t, &typed));
+  out.resize(want);
+  if (typed) {
+    napi_typedarray_type ty; size_t len = 0; void* data = nullptr; napi_value ab; size_t off = 0;
+    NAPI_OK(napi_get_typedarray_info(env, t, &ty, &len, &data, &ab, &off));
+    if ((ty != napi_uint8_clamped_array && ty != napi_uint8_array) || len < want) throw Fail{"texels: need >= width*height*4 bytes"};
+    memcpy(out.data(), data, want);
+    return;
+  }
+  uint32_t len = 0;
+  NAPI_OK(napi_get_array_length(env, t, &len));
+  if (len < want) throw Fail{"texels: need >= width*height*4 entries"};
+  for (size_t i = 0; i < want; i++) {
+    napi_value e;
+    NAPI_OK(napi_get_element(env, t, (uint32_t)i, &e));
+    const double v = num(env, e);
+    out[i] = (uint8_t)(!(v > 0) ? 0 : (v >= 255 ? 255 : std::nearbyint(v)));
+  }
+}
+
+// render(scene, camera, opts, out): scene = { objects: [{origin, r2, mtl:{color, albedo, specular_exponent,
+// refract_index, sampler_kind?, texture_unit?, checker_freq?, checker_color?, star_threshold?, star_gain?}}],
+// textures: [{width, height, texels}], lights?, light_intensity?, eps? }
+napi_value Render(napi_env env, napi_callback_info info) {
+  napi_value undef;
+  napi_get_undefined(env, &undef);
+  rtb_scene_t scene = nullptr;
+  try {
+    size_t argc = 4;
+    napi_value argv[4];
+    NAPI_OK(napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+    if (argc < 4) throw Fail{"render(scene, camera, opts, out) takes 4 arguments"};
+
+    // ---- scene ------------------------------------------------------------------------------------
+    napi_value objects = prop(env, argv[0], "objects");
+    uint32_t n = 0;
+    NAPI_OK(napi_get_array_length(env, objects, &n));
+    std::vector<RtbSphere> spheres(n);
+    for (uint32_t i = 0; i < n; i++) {
+      napi_value o, m;
+      NAPI_OK(napi_get_element(env, objects, i, &o));
+      RtbSphere& s = spheres[i];
+      memset(&s, 0, sizeof s);
+      vec(env, o, "origin", s.origin, 3);
+      s.r2 = num_prop(env, o, "r2", 0, true);                       // createSphere stores r*r (main.js:413)
+      m = prop(env, o, "mtl");
+      vec(env, m, "color", s.mtl.color, 3);
+      vec(env, m, "albedo", s.mtl.albedo, 5);
+      s.mtl.specular_exponent = num_prop(env, m, "specular_exponent", 0, true);
+      s.mtl.refract_index = num_prop(env, m, "refract_index", 1, true);
+      s.mtl.sampler_kind = (int32_t)num_prop(env, m, "sampler_kind", RTB_SAMPLER_COLOR);
+      s.mtl.texture_unit = (int32_t)num_prop(env, m, "texture_unit", 0);
+      s.mtl.checker_freq[0] = 5000; s.mtl.checker_freq[1] = 2500;    // main.js:129-131 defaults
+      const double c0[3] = {1, 1, 0}, c1[3] = {1, 0, 1};
+      memcpy(s.mtl.checker_color[0], c0, sizeof c0);
+      memcpy(s.mtl.checker_color[1], c1, sizeof c1);
+      s.mtl.star_threshold = num_prop(env, m, "star_threshold", 0.001);
+      s.mtl.star_gain = num_prop(env, m, "star_gain", 1000);
+      if (has(env, m, "checker_freq")) vec(env, m, "checker_freq", s.mtl.checker_freq, 2);
+    }
+    std::vector<RtbTexture> textures;
+    std::vector<std::vector<uint8_t>> texel_store;
+    if (has(env, argv[0], "textures")) {
+      napi_value ts = prop(env, argv[0], "textures");
+      uint32_t nt = 0;
+      NAPI_OK(napi_get_array_length(env, ts, &nt));
+      textures.resize(nt);
+      texel_store.resize(nt);
+      for (uint32_t i = 0; i < nt; i++) {
+        napi_value t;
+        NAPI_OK(napi_get_element(env, ts, i, &t));
+        textures[i].width = (int32_t)num_prop(env, t, "width", 0, true);
+        textures[i].height = (int32_t)num_prop(env, t, "height", 0, true);
+        if (textures[i].width <= 0 || textures[i].height <= 0) throw Fail{"texture not loaded (width/height 0)"};
+        read_texels(env, prop(env, t, "texels"), (size_t)textures[i].width * textures[i].height * 4, texel_store[i]);
+        textures[i].texels = texel_store[i].data();
+      }
+    }
+    RtbSceneDesc desc;
+    memset(&desc, 0, sizeof desc);
+    desc.abi_version = RTB_ABI_VERSION;
+    desc.n_spheres = (int32_t)n;
+    desc.spheres = spheres.data();
+    desc.n_textures = (int32_t)textures.size();
+    desc.textures = textures.data();
+    const double dl[2][3] = {{5, 10, 5}, {5, 10, 0}};                 // main.js:283
+    desc.n_lights = 2;
+    memcpy(desc.lights, dl, sizeof dl);
+    if (has(env, argv[0], "lights")) {
+      napi_value ls = prop(env, argv[0], "lights");
+      uint32_t nl = 0;
+      NAPI_OK(napi_get_array_length(env, ls, &nl));
+      if (nl > RTB_MAX_LIGHTS) throw Fail{"too many lights"};
+      desc.n_lights = (int32_t)nl;
+      for (uint32_t i = 0; i < nl; i++) {
+        napi_value l;
+        NAPI_OK(napi_get_element(env, ls, i, &l));
+        for (uint32_t c = 0; c < 3; c++) {
+          napi_value e;
+          NAPI_OK(napi_get_element(env, l, c, &e));
+          desc.lights[i][c] = num(env, e);
+        }
+      }
+    }
+    desc.light_intensity = num_prop(env, argv[0], "light_intensity", 50);   // main.js:284
+    desc.eps = num_prop(env, argv[0], "eps", 0.001);                        // main.js:430-445
+
+    // ---- camera -----------------------------------------------------------------------------------
+    RtbCamera cam;
+    memset(&cam, 0, sizeof cam);
+    cam.width = (int32_t)num_prop(env, argv[1], "width", 0, true);
+    cam.height = (int32_t)num_prop(env, argv[1], "height", 0, true);
+    vec(env, argv[1], "origin", cam.origin, 3);
+    vec(env, argv[1], "axisX", cam.axisX, 3);
+    vec(env, argv[1], "axisY", cam.axisY, 3);
+    vec(env, argv[1], "axisZ", cam.axisZ, 3);
+    cam.projW = num_prop(env, argv[1], "projW", 0, true);
+    cam.projH = num_prop(env, argv[1], "projH", 0, true);
+    cam.projD = num_prop(env, argv[1], "projD", 0, true);
+    cam.camera_mode = (int32_t)num_prop(env, argv[1], "camera_mode", RTB_CAMERA_REFERENCE);
+
+    // ---- options ----------------------------------------------------------------------------------
+    RtbRenderOpts o;
+    rtb_default_opts(&o);
+    o.segs = (int32_t)num_prop(env, argv[2], "segs", 8);                    // main.js:194
+    o.spp_grid = (int32_t)num_prop(env, argv[2], "spp_grid", 1);
+    o.precision = (int32_t)num_prop(env, argv[2], "precision", RTB_PRECISION_FP32);
+    o.kernel = (int32_t)num_prop(env, argv[2], "kernel", RTB_KERNEL_AUTO);
+    o.star_mode = (int32_t)num_prop(env, argv[2], "star_mode", RTB_STARS_OFF);
+    o.y0 = (int32_t)num_prop(env, argv[2], "y0", 0);                        // progressive rows (main.js:200-201)
+    o.y1 = (int32_t)num_prop(env, argv[2], "y1", 0);
+
+    // ---- output: colorbuf.data, a Uint8ClampedArray(W*H*4) (main.js:83) ----------------------------
+    bool typed = false;
+    NAPI_OK(napi_is_typedarray(env, argv[3], &typed));
+    if (!typed) throw Fail{"out must be a Uint8ClampedArray"};
+    napi_typedarray_type ty; size_t len = 0; void* data = nullptr; napi_value ab; size_t off = 0;
+    NAPI_OK(napi_get_typedarray_info(env, argv[3], &ty, &len, &data, &ab, &off));
+    if (ty != napi_uint8_clamped_array && ty != napi_uint8_array) throw Fail{"out must be a Uint8ClampedArray"};
+    if (len < (size_t)cam.width * cam.height * 4) throw Fail{"out is smaller than width*height*4"};
+
+    if (rtb_init(-1) != RTB_OK) throw Fail{rtb_last_error()};
+    if (rtb_scene_create(&desc, &scene) != RTB_OK) throw Fail{rtb_last_error()};
+    RtbStats st;
+    if (rtb_render(scene, &cam, &o, (uint8_t*)data, &st) != RTB_OK) throw Fail{rtb_last_error()};
+    rtb_scene_destroy(scene);
+    scene = nullptr;
+
+    napi_value res, v;
+    NAPI_OK(napi_create_object(env, &res));
+    NAPI_OK(napi_create_double(env, st.kernel_ms, &v)); NAPI_OK(napi_set_named_property(env, res, "kernel_ms", v));
+    NAPI_OK(napi_create_double(env, st.d2h_ms, &v)); NAPI_OK(napi_set_named_property(env, res, "d2h_ms", v));
+    NAPI_OK(napi_create_double(env, (double)st.nodes, &v)); NAPI_OK(napi_set_named_property(env, res, "nodes", v));
+    NAPI_OK(napi_create_double(env, (double)st.shadow_rays, &v)); NAPI_OK(napi_set_named_property(env, res, "shadow_rays", v));
+    NAPI_OK(napi_create_double(env, (double)st.launches, &v)); NAPI_OK(napi_set_named_property(env, res, "launches", v));
+    return res;
+  } catch (const Fail& f) {
+    if (scene) rtb_scene_destroy(scene);
+    napi_throw_error(env, nullptr, f.msg.c_str());          // JS `Error`; nothing crosses as a C++ exception
+    return undef;
+  }
+}
+
+napi_value Version(napi_env env, napi_callback_info) {
+  napi_value v;
+  napi_create_string_utf8(env, rtb_version(), NAPI_AUTO_LENGTH, &v);
+  return v;
+}
+
+}  // namespace
+
+// The well-known entry symbol Node resolves with dlsym() after dlopen()ing the .node file.
+extern "C" __attribute__((visibility("default"))) napi_value napi_register_module_v1(napi_env env, napi_value exports) {
+  napi_value fn;
+  if (napi_create_function(env, "render", NAPI_AUTO_LENGTH, Render, nullptr, &fn) == napi_ok)
+    napi_set_named_property(env, exports, "render", fn);
+  if (napi_create_function(env, "version", NAPI_AUTO_LENGTH, Version, nullptr, &fn) == napi_ok)
+    napi_set_named_property(env, exports, "version", fn);
+  return exports;
+}
