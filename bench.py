@@ -235,25 +235,37 @@ def main():
     host = torch.empty((H, W, 4), dtype=torch.uint8).pin_memory()
     e2e_launches = 0
 
+    import ctypes as C
+    lib = A.load()
+    desc = renderer.desc                    # the scene description in HOST memory, marshalled once
+    cam_c = cam.to_c()
+    e2e_opts = rt.make_opts(**opts_kw)
+    h2d_bytes = 0
+
     def e2e_step():
-        nonlocal e2e_launches
-        if world <= 1:
-            with rt.Renderer(objs, device=local_rank) as r2:     # H2D: scene description
-                st = A.RtbStats()
-                r2.redraw_ptr(cam, rt.make_opts(**opts_kw), host.data_ptr(), st)   # D2H: framebuffer
+        """rtb_scene_create (H2D: the whole scene description) -> render -> frame in pinned host memory."""
+        nonlocal e2e_launches, h2d_bytes
+        h = C.c_void_p()
+        A.check(lib.rtb_scene_create(C.byref(desc.c), C.byref(h)))
+        h2d_bytes = int(lib.rtb_scene_h2d_bytes(h)) + 2 * 16 * ((cnt["n_spheres"] + 15) // 16 * 16)   # + primary tables
+        st = A.RtbStats()
+        try:
+            if world <= 1:
+                A.check(lib.rtb_render(h, C.byref(cam_c), C.byref(e2e_opts), host.data_ptr(), C.byref(st)))   # D2H inside
                 e2e_launches += st.launches
-        else:
-            with rt.Renderer(objs, device=local_rank) as r2:
-                sr2 = sr
-                old = sr2.r
-                sr2.r = r2
-                st = A.RtbStats()
-                frame = sr2.redraw(cam, stats=st, **opts_kw)
-                sr2.r = old
+            else:
+                old = sr.r._h
+                sr.r._h = h
+                try:
+                    frame = sr.redraw(cam, stats=st, **opts_kw)
+                finally:
+                    sr.r._h = old
                 e2e_launches += st.launches + 1
                 if rank == 0:
                     host.copy_(frame, non_blocking=True)
                 torch.cuda.synchronize()
+        finally:
+            lib.rtb_scene_destroy(h)
 
     e2e_step()
     barrier()
@@ -325,8 +337,9 @@ def main():
         "roofline": roofline,
         "e2e": {"value": round(e2e_value, 2), "unit": "Mrays/s", "ms_per_step": round(e2e_ms, 4),
                 "frames_per_s": round(1000.0 / e2e_ms, 3),
-                "h2d_bytes_per_step": scene_h2d_bytes(renderer.desc), "d2h_bytes_per_step": W * H * 4,
-                "what": "rtb_scene_create (scene from host) + rtb_render into a pinned host buffer + destroy"},
+                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": W * H * 4,
+                "what": "per step: rtb_scene_create (whole scene description from host memory) + rtb_render into a "
+                        "pinned host buffer + rtb_scene_destroy"},
         "gpu_launches": int(st_acc["launches"] + e2e_launches),
         "clocks": clocks,
         "device": info,

@@ -320,6 +320,8 @@ void rtb_shutdown(void) {
   for (int i = 0; i < 2; i++) { cudaEventDestroy(g_rtb.frame_done[i]); cudaEventDestroy(g_rtb.copy_done[i]); }
   for (int i = 0; i < g_rtb.n_timers; i++) cudaEventDestroy(g_rtb.timers[i]);
   cudaFree(g_rtb.d_frame[0]); cudaFree(g_rtb.d_frame[1]); cudaFree(g_rtb.d_counters);
+  cudaFree(g_rtb.cached_arena);
+  if (g_rtb.h_stage) cudaFreeHost(g_rtb.h_stage);
   wf_free();
   (void)cudaGetLastError();
   g_rtb = RtbGlobal{};
@@ -339,29 +341,14 @@ int rtb_scene_create(const RtbSceneDesc* d, rtb_scene_t* out) {
   s->spheres.assign(d->spheres, d->spheres + n);
   memcpy(s->lights, d->lights, sizeof s->lights);
   const int na = n > 0 ? n : 1;
+  const int np = wf_pad(na);
+  const int nt = d->n_textures > 0 ? d->n_textures : 1;
+  s->n_pad = np;
 
-  std::vector<double> g64((size_t)na * 4);
-  std::vector<float> g32((size_t)na * 4);
-  std::vector<DevMaterial<double>> m64(na);
-  std::vector<DevMaterial<float>> m32(na);
-  for (int i = 0; i < n; i++) {
-    const RtbSphere& sp = d->spheres[i];
-    for (int c = 0; c < 3; c++) { g64[4 * i + c] = sp.origin[c]; g32[4 * i + c] = (float)sp.origin[c]; }
-    g64[4 * i + 3] = sp.r2; g32[4 * i + 3] = (float)sp.r2;
-    fill_material(m64[i], sp.mtl);
-    fill_material(m32[i], sp.mtl);
-  }
-  RTB_CUDA(cudaMalloc(&s->d_geom64, g64.size() * sizeof(double)));
-  RTB_CUDA(cudaMalloc(&s->d_geom32, g32.size() * sizeof(float)));
-  RTB_CUDA(cudaMalloc(&s->d_mtl64, m64.size() * sizeof(DevMaterial<double>)));
-  RTB_CUDA(cudaMalloc(&s->d_mtl32, m32.size() * sizeof(DevMaterial<float>)));
-  RTB_CUDA(cudaMemcpy(s->d_geom64, g64.data(), g64.size() * sizeof(double), cudaMemcpyHostToDevice));
-  RTB_CUDA(cudaMemcpy(s->d_geom32, g32.data(), g32.size() * sizeof(float), cudaMemcpyHostToDevice));
-  RTB_CUDA(cudaMemcpy(s->d_mtl64, m64.data(), m64.size() * sizeof(DevMaterial<double>), cudaMemcpyHostToDevice));
-  RTB_CUDA(cudaMemcpy(s->d_mtl32, m32.data(), m32.size() * sizeof(DevMaterial<float>), cudaMemcpyHostToDevice));
-
-  // textures: one uchar4 pool, byte-exact copies of the caller's RGBA8 texels
-  std::vector<DevTexture> tex(d->n_textures > 0 ? d->n_textures : 1);
+  // One device arena for everything the scene owns, filled from one pinned staging buffer with one
+  // H2D copy.  Both are cached in the library between scenes, so handing a scene over per frame costs
+  // a memcpy + a DMA, not a dozen cudaMalloc/cudaFree calls.
+  std::vector<DevTexture> tex(nt);
   size_t pool = 0;
   for (int t = 0; t < d->n_textures; t++) {
     tex[t].width = d->textures[t].width; tex[t].height = d->textures[t].height;
@@ -369,34 +356,76 @@ int rtb_scene_create(const RtbSceneDesc* d, rtb_scene_t* out) {
     pool += (size_t)tex[t].width * tex[t].height;
   }
   if (pool > 0xffffffffull) { rtb_set_error("texture pool too large"); return RTB_ERR_INVALID; }
-  RTB_CUDA(cudaMalloc(&s->d_tex, tex.size() * sizeof(DevTexture)));
-  RTB_CUDA(cudaMemcpy(s->d_tex, tex.data(), tex.size() * sizeof(DevTexture), cudaMemcpyHostToDevice));
-  RTB_CUDA(cudaMalloc(&s->d_texels, (pool > 0 ? pool : 1) * sizeof(uchar4)));
-  for (int t = 0; t < d->n_textures; t++)
-    RTB_CUDA(cudaMemcpy(s->d_texels + tex[t].offset, d->textures[t].texels,
-                        (size_t)tex[t].width * tex[t].height * 4, cudaMemcpyHostToDevice));
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
+  const size_t o_g64 = take((size_t)na * 4 * sizeof(double));
+  const size_t o_g32 = take((size_t)na * 4 * sizeof(float));
+  const size_t o_m64 = take((size_t)na * sizeof(DevMaterial<double>));
+  const size_t o_m32 = take((size_t)na * sizeof(DevMaterial<float>));
+  const size_t o_tex = take((size_t)nt * sizeof(DevTexture));
+  const size_t o_txl = take((pool > 0 ? pool : 1) * sizeof(uchar4));
+  const size_t tb = (size_t)np * sizeof(float4);
+  size_t o_ltab[RTB_MAX_LIGHTS], o_lx[RTB_MAX_LIGHTS];
+  for (int k = 0; k < d->n_lights; k++) { o_ltab[k] = take(tb); o_lx[k] = take(tb); }
+  const size_t o_gtab = take(tb);
+  const size_t upload_bytes = off;                       // everything above is written by this call
+  const size_t o_ptab = take(tb), o_px = take(tb);       // primary tables: filled per camera
+  const size_t total = off;
 
+  if (g_rtb.cached_arena && g_rtb.cached_arena_bytes >= total) {
+    s->arena = g_rtb.cached_arena; s->arena_bytes = g_rtb.cached_arena_bytes;
+    g_rtb.cached_arena = nullptr; g_rtb.cached_arena_bytes = 0;
+  } else {
+    RTB_CUDA(cudaMalloc(&s->arena, total));
+    s->arena_bytes = total;
+  }
+  const size_t stage_need = upload_bytes > 2 * tb ? upload_bytes : 2 * tb;
+  if (g_rtb.stage_bytes < stage_need) {
+    if (g_rtb.h_stage) { RTB_CUDA(cudaStreamSynchronize(g_rtb.stream)); cudaFreeHost(g_rtb.h_stage); }
+    g_rtb.h_stage = nullptr; g_rtb.stage_bytes = 0;
+    RTB_CUDA(cudaMallocHost(&g_rtb.h_stage, stage_need));
+    g_rtb.stage_bytes = stage_need;
+  }
+  char* hs = g_rtb.h_stage;
+  char* ds = s->arena;
+  double* g64 = reinterpret_cast<double*>(hs + o_g64);
+  float* g32 = reinterpret_cast<float*>(hs + o_g32);
+  DevMaterial<double>* m64 = reinterpret_cast<DevMaterial<double>*>(hs + o_m64);
+  DevMaterial<float>* m32 = reinterpret_cast<DevMaterial<float>*>(hs + o_m32);
+  for (int i = 0; i < n; i++) {
+    const RtbSphere& sp = d->spheres[i];
+    for (int c = 0; c < 3; c++) { g64[4 * i + c] = sp.origin[c]; g32[4 * i + c] = (float)sp.origin[c]; }
+    g64[4 * i + 3] = sp.r2; g32[4 * i + 3] = (float)sp.r2;
+    fill_material(m64[i], sp.mtl);
+    fill_material(m32[i], sp.mtl);
+  }
+  memcpy(hs + o_tex, tex.data(), (size_t)nt * sizeof(DevTexture));
+  for (int t = 0; t < d->n_textures; t++)                // byte-exact copies of the caller's RGBA8 texels
+    memcpy(hs + o_txl + (size_t)tex[t].offset * 4, d->textures[t].texels, (size_t)tex[t].width * tex[t].height * 4);
+  // wavefront per-light tables (fp64 arithmetic, one rounding to fp32) and the general-ray table
+  for (int k = 0; k < d->n_lights; k++)
+    wf_make_table(d->spheres, n, np, d->lights[k], reinterpret_cast<float4*>(hs + o_ltab[k]),
+                  reinterpret_cast<float4*>(hs + o_lx[k]));
+  wf_make_geom_table(d->spheres, n, np, reinterpret_cast<float4*>(hs + o_gtab));
+  RTB_CUDA(cudaMemcpyAsync(ds, hs, upload_bytes, cudaMemcpyHostToDevice, g_rtb.stream));
+  RTB_CUDA(cudaStreamSynchronize(g_rtb.stream));         // staging is reused; the scene is usable on any stream
+  s->h2d_bytes = upload_bytes;
+
+  s->d_geom64 = reinterpret_cast<double*>(ds + o_g64);
+  s->d_geom32 = reinterpret_cast<float*>(ds + o_g32);
+  s->d_mtl64 = reinterpret_cast<DevMaterial<double>*>(ds + o_m64);
+  s->d_mtl32 = reinterpret_cast<DevMaterial<float>*>(ds + o_m32);
+  s->d_tex = reinterpret_cast<DevTexture*>(ds + o_tex);
+  s->d_texels = reinterpret_cast<uchar4*>(ds + o_txl);
+  for (int k = 0; k < d->n_lights; k++) {
+    s->d_light_tab[k] = reinterpret_cast<float4*>(ds + o_ltab[k]);
+    s->d_light_x[k] = reinterpret_cast<float4*>(ds + o_lx[k]);
+  }
+  s->d_geom_tab = reinterpret_cast<float4*>(ds + o_gtab);
+  s->d_primary_tab = reinterpret_cast<float4*>(ds + o_ptab);
+  s->d_primary_x = reinterpret_cast<float4*>(ds + o_px);
   fill_scene_view<double>(s->sc64, s, d, s->d_geom64, s->d_mtl64);
   fill_scene_view<float>(s->sc32, s, d, s->d_geom32, s->d_mtl32);
-
-  // wavefront per-light tables (fp64 arithmetic, one rounding to fp32)
-  const int np = wf_pad(na);
-  s->n_pad = np;
-  std::vector<float4> tab(np), exact(np);
-  const size_t tb = (size_t)np * sizeof(float4);
-  for (int k = 0; k < d->n_lights; k++) {
-    wf_make_table(d->spheres, n, np, d->lights[k], tab.data(), exact.data());
-    RTB_CUDA(cudaMalloc(&s->d_light_tab[k], tb));
-    RTB_CUDA(cudaMalloc(&s->d_light_x[k], tb));
-    RTB_CUDA(cudaMemcpy(s->d_light_tab[k], tab.data(), tb, cudaMemcpyHostToDevice));
-    RTB_CUDA(cudaMemcpy(s->d_light_x[k], exact.data(), tb, cudaMemcpyHostToDevice));
-  }
-  wf_make_geom_table(d->spheres, n, np, tab.data());
-  RTB_CUDA(cudaMalloc(&s->d_geom_tab, tb));
-  RTB_CUDA(cudaMemcpy(s->d_geom_tab, tab.data(), tb, cudaMemcpyHostToDevice));
-  RTB_CUDA(cudaMalloc(&s->d_primary_tab, tb));
-  RTB_CUDA(cudaMalloc(&s->d_primary_x, tb));
-  RTB_CUDA(cudaMallocHost(&s->h_primary_tab, 2 * tb));
   guard.s = nullptr;
   *out = s;
   return RTB_OK;
@@ -404,15 +433,28 @@ int rtb_scene_create(const RtbSceneDesc* d, rtb_scene_t* out) {
 
 void rtb_scene_destroy(rtb_scene_t s) {
   if (!s) return;
-  if (g_rtb.inited) cudaDeviceSynchronize();
-  cudaFree(s->d_geom64); cudaFree(s->d_geom32); cudaFree(s->d_mtl64); cudaFree(s->d_mtl32);
-  cudaFree(s->d_tex); cudaFree(s->d_texels);
-  for (int k = 0; k < RTB_MAX_LIGHTS; k++) { cudaFree(s->d_light_tab[k]); cudaFree(s->d_light_x[k]); }
-  cudaFree(s->d_geom_tab); cudaFree(s->d_primary_tab); cudaFree(s->d_primary_x);
-  if (s->h_primary_tab) cudaFreeHost(s->h_primary_tab);
+  if (s->arena) {
+    if (g_rtb.inited) {
+      // renders are synchronous w.r.t. the host except rtb_render_device on a caller stream: drain
+      cudaDeviceSynchronize();
+      if (!g_rtb.cached_arena) {                          // keep one arena for the next scene
+        g_rtb.cached_arena = s->arena; g_rtb.cached_arena_bytes = s->arena_bytes;
+      } else if (g_rtb.cached_arena_bytes < s->arena_bytes) {
+        cudaFree(g_rtb.cached_arena);
+        g_rtb.cached_arena = s->arena; g_rtb.cached_arena_bytes = s->arena_bytes;
+      } else {
+        cudaFree(s->arena);
+      }
+    } else {
+      cudaFree(s->arena);
+    }
+  }
   (void)cudaGetLastError();
   delete s;
 }
+
+
+uint64_t rtb_scene_h2d_bytes(rtb_scene_t s) { return s ? (uint64_t)s->h2d_bytes : 0; }
 
 int rtb_render_device(rtb_scene_t s, const RtbCamera* cam, const RtbRenderOpts* o, void* d_out,
                       void* cuda_stream, RtbStats* stats) {

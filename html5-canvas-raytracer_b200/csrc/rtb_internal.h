@@ -59,7 +59,9 @@ struct RtbScene_ {
   float4* d_light_x[RTB_MAX_LIGHTS] = {nullptr, nullptr, nullptr, nullptr};     // exact (L, c), per light
   float4* d_primary_tab = nullptr;        // packed, per camera origin
   float4* d_primary_x = nullptr;          // exact (L, c)
-  float4* h_primary_tab = nullptr;        // pinned staging: n_pad packed + n_pad exact float4
+  char* arena = nullptr;                  // single device allocation all the pointers above point into
+  size_t arena_bytes = 0;
+  size_t h2d_bytes = 0;                   // bytes rtb_scene_create uploaded
   double primary_origin[3] = {0, 0, 0};
   bool primary_valid = false;
 };
@@ -82,6 +84,10 @@ struct RtbGlobal {
   int wf_lights = 0;                          // shadow queues allocated
   size_t wf_bytes = 0;
   unsigned long long* d_counters = nullptr;   // 3 x u64 for the pixel kernels
+  char* cached_arena = nullptr;               // last destroyed scene's device arena, reused by the next create
+  size_t cached_arena_bytes = 0;
+  char* h_stage = nullptr;                    // pinned staging for scene uploads and per-camera tables
+  size_t stage_bytes = 0;
   // per-kernel-class event pool for RtbStats.ms_* (only used when stats are requested)
   static const int kMaxTimers = 256;
   cudaEvent_t timers[kMaxTimers] = {};

@@ -768,9 +768,10 @@ int wf_render(RtbScene_* s, const RtbCamera* cam, const DevFrameT<float>& fr32, 
   // primary tables: per-sphere constants of rays leaving the camera origin, in fp64, rounded once
   if (!s->primary_valid || s->primary_origin[0] != cam->origin[0] || s->primary_origin[1] != cam->origin[1] ||
       s->primary_origin[2] != cam->origin[2]) {
-    float4* h_x = s->h_primary_tab + n_pad;
-    wf_make_table(s->spheres.data(), n, n_pad, cam->origin, s->h_primary_tab, h_x);
-    RTB_CUDA(cudaMemcpyAsync(s->d_primary_tab, s->h_primary_tab, smem, cudaMemcpyHostToDevice, st));
+    float4* h_tab = reinterpret_cast<float4*>(g_rtb.h_stage);       // sized >= 2 tables by rtb_scene_create
+    float4* h_x = h_tab + n_pad;
+    wf_make_table(s->spheres.data(), n, n_pad, cam->origin, h_tab, h_x);
+    RTB_CUDA(cudaMemcpyAsync(s->d_primary_tab, h_tab, smem, cudaMemcpyHostToDevice, st));
     RTB_CUDA(cudaMemcpyAsync(s->d_primary_x, h_x, smem, cudaMemcpyHostToDevice, st));
     // the pinned staging buffer is rewritten by the next camera: wait for the copy
     RTB_CUDA(cudaStreamSynchronize(st));

@@ -175,6 +175,8 @@ void rtb_shutdown(void);
  * Replaces: the `objects` array + `texture_unit*` closures of main() (main.js:107-163). */
 int rtb_scene_create(const RtbSceneDesc* desc, rtb_scene_t* out);
 void rtb_scene_destroy(rtb_scene_t scene);
+/* Bytes rtb_scene_create copied host -> device for this scene (geometry, materials, textures, tables). */
+uint64_t rtb_scene_h2d_bytes(rtb_scene_t scene);
 
 /* Render one frame into a caller-owned HOST buffer of width*height*4 bytes (RGBA8, row-major,
  * A = 255): exactly the bytes `colorbuf.data` holds after the last `spanish` tick.
