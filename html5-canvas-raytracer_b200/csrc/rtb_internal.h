@@ -146,12 +146,26 @@ inline void wf_make_table(const RtbSphere* sp, int n, int n_pad, const double or
     exact[i] = make_float4((float)L0, (float)L1, (float)L2, (float)cc);
   }
 }
+// The fast test evaluates e = a^2 + b^2 - r2' with a = u.C - u.org, b = v.C - v.org in fp32.  Near the
+// decision boundary |a|,|b| <= r and the absolute error of a, b is a few ulp of (|C| + |org|), so
+// err(e) <~ 1e-6 r (|C| + R), R = bound on |org| (ray origins lie on sphere surfaces).  r2' carries that
+// margin so that rounding can only ADD candidates.
 inline void wf_make_geom_table(const RtbSphere* sp, int n, int n_pad, float4* tab) {
   const float inf = __builtin_huge_valf();
+  double R = 0;
+  for (int i = 0; i < n; i++) {
+    const double c = __builtin_sqrt(sp[i].origin[0] * sp[i].origin[0] + sp[i].origin[1] * sp[i].origin[1] +
+                                    sp[i].origin[2] * sp[i].origin[2]);
+    const double e = c + __builtin_sqrt(sp[i].r2 > 0 ? sp[i].r2 : 0);
+    if (e > R) R = e;
+  }
   for (int i = 0; i < n_pad; i++) {
     if (i >= n) { wf_pack(tab, i, 0.f, 0.f, 0.f, inf); continue; }
+    const double c = __builtin_sqrt(sp[i].origin[0] * sp[i].origin[0] + sp[i].origin[1] * sp[i].origin[1] +
+                                    sp[i].origin[2] * sp[i].origin[2]);
+    const double r = __builtin_sqrt(sp[i].r2 > 0 ? sp[i].r2 : 0);
     wf_pack(tab, i, (float)sp[i].origin[0], (float)sp[i].origin[1], (float)sp[i].origin[2],
-            -(float)(sp[i].r2 * (1.0 + 2e-6)));
+            -(float)(sp[i].r2 * (1.0 + 2e-6) + 2e-6 * r * (c + R)));
   }
 }
 

@@ -149,9 +149,13 @@ __device__ __noinline__ unsigned long long slow_primary(const float4* __restrict
   return best;
 }
 
-__device__ __noinline__ unsigned long long slow_general(const float4* __restrict__ geom, int j, uint32_t m,
-                                                        float nox, float noy, float noz, float dx, float dy,
-                                                        float dz, float eps, unsigned long long best) {
+// The ray itself (origin, direction) is re-read from the queue: the fast path only keeps its (u, v, ku, kv).
+__device__ __noinline__ unsigned long long slow_general(const float4* __restrict__ geom,
+                                                        const float4* __restrict__ ray_o,
+                                                        const float4* __restrict__ ray_d, int j, uint32_t m,
+                                                        uint32_t node, float eps, unsigned long long best) {
+  const float4 ro = ray_o[node], rd = ray_d[node];
+  const float nox = -ro.x, noy = -ro.y, noz = -ro.z, dx = ro.w, dy = rd.x, dz = rd.y;
   while (m) {
     const int b = 31 - __clz((int)m);
     m ^= 1u << b;
@@ -228,31 +232,34 @@ RTB_DEVINL void sweep_primary(const float4* __restrict__ tab, const float4* __re
   }
 }
 
-// General closest hit (reflect / refract rays): the reference's test d2 = |L|^2 - tca^2 <= r2
-// (main.js:422-425), two spheres per packed instruction: 3 FADD2 + 7 FFMA2/FMUL2 per pair per ray.
+// General closest hit (reflect / refract rays).  The reference tests d2 = |L|^2 - tca^2 <= r2
+// (main.js:422-425); with two unit vectors u, v that complete dir to an orthonormal basis,
+// d2 = (u.L)^2 + (v.L)^2 EXACTLY (L = tca dir + (u.L) u + (v.L) v), which needs neither L nor tca and has
+// no cancellation between |L|^2 and tca^2 (r = 500 / 5000 spheres).  With ku = u.org, kv = v.org per
+// ray:  a = u.C - ku, b = v.C - kv, e = a^2 + b^2 - r2'  ->  8 FFMA2 per sphere pair per ray.
 template <int R>
-RTB_DEVINL void sweep_general(const float4* __restrict__ tab, const float4* __restrict__ geom, int n_pad,
-                              const float (&no)[R][3], const float (&d)[R][3], const bool (&active)[R],
+RTB_DEVINL void sweep_general(const float4* __restrict__ tab, const float4* __restrict__ geom,
+                              const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, int n_pad,
+                              const float (&u)[R][3], const float (&v)[R][3], const float (&nku)[R],
+                              const float (&nkv)[R], const uint32_t (&node)[R], const bool (&active)[R],
                               unsigned long long (&best)[R], float eps) {
   uint32_t mask[R];
 #pragma unroll
   for (int q = 0; q < R; q++) { best[q] = KEY_NONE; mask[q] = 0; }
   for (int j = 0; j < n_pad; j += WF_GROUP) {
 #pragma unroll
-    for (int u = 0; u < WF_GROUP / 2; u++) {
-      const float4 A = tab[j + 2 * u], B = tab[j + 2 * u + 1];
+    for (int p = 0; p < WF_GROUP / 2; p++) {
+      const float4 A = tab[j + 2 * p], B = tab[j + 2 * p + 1];
 #pragma unroll
       for (int q = 0; q < R; q++) {
-        const float2 L0 = __fadd2_rn(f2(A.x, A.y), f2(no[q][0], no[q][0]));   // C - org
-        const float2 L1 = __fadd2_rn(f2(A.z, A.w), f2(no[q][1], no[q][1]));
-        const float2 L2 = __fadd2_rn(f2(B.x, B.y), f2(no[q][2], no[q][2]));
-        float2 tca = __fmul2_rn(f2(d[q][2], d[q][2]), L2);
-        tca = __ffma2_rn(f2(d[q][1], d[q][1]), L1, tca);
-        tca = __ffma2_rn(f2(d[q][0], d[q][0]), L0, tca);
-        float2 e = __ffma2_rn(L2, L2, f2(B.z, B.w));                          // |L|^2 - r2'
-        e = __ffma2_rn(L1, L1, e);
-        e = __ffma2_rn(L0, L0, e);
-        e = __ffma2_rn(f2(-tca.x, -tca.y), tca, e);                           // d2 - r2' <= 0: candidate
+        float2 a = __ffma2_rn(f2(u[q][2], u[q][2]), f2(B.x, B.y), f2(nku[q], nku[q]));
+        a = __ffma2_rn(f2(u[q][1], u[q][1]), f2(A.z, A.w), a);
+        a = __ffma2_rn(f2(u[q][0], u[q][0]), f2(A.x, A.y), a);
+        float2 b = __ffma2_rn(f2(v[q][2], v[q][2]), f2(B.x, B.y), f2(nkv[q], nkv[q]));
+        b = __ffma2_rn(f2(v[q][1], v[q][1]), f2(A.z, A.w), b);
+        b = __ffma2_rn(f2(v[q][0], v[q][0]), f2(A.x, A.y), b);
+        float2 e = __ffma2_rn(a, a, f2(B.z, B.w));                             // a^2 - r2'
+        e = __ffma2_rn(b, b, e);                                               // d2 - r2' <= 0: candidate
         mask[q] = push_sign(push_sign(mask[q], e.x), e.y);
       }
     }
@@ -263,8 +270,7 @@ RTB_DEVINL void sweep_general(const float4* __restrict__ tab, const float4* __re
 #pragma unroll
       for (int q = 0; q < R; q++) {
         const uint32_t m = mask[q] & 0xffu;
-        if (m && active[q])
-          best[q] = slow_general(geom, j, m, no[q][0], no[q][1], no[q][2], d[q][0], d[q][1], d[q][2], eps, best[q]);
+        if (m && active[q]) best[q] = slow_general(geom, ray_o, ray_d, j, m, node[q], eps, best[q]);
       }
     }
   }
@@ -448,17 +454,21 @@ wf_trace_kernel(const __grid_constant__ WfParams P, int level) {
   for (;;) {
     const uint64_t base = (uint64_t)begin + (uint64_t)next_chunk(&P.b.ctr->work_trace[level], lane) * CHUNK;
     if (base >= end) break;
-    float a[R][3], b[R][3];          // PRIMARY: a = -dir;  general: a = -org, b = dir
+    float a[R][3], b[R][3];          // PRIMARY: a = -dir;  general: a = u, b = v (basis completing dir)
+    float nku[R], nkv[R];            // general: -(u.org), -(v.org)
+    uint32_t nodes[R];
     bool active[R];
     unsigned long long best[R];
 #pragma unroll
     for (int q = 0; q < R; q++) {
       const uint32_t node = (uint32_t)base + (uint32_t)q * 32u + lane;
+      nodes[q] = node;
       active[q] = node < end;
-      // idle slots must never look like candidates: zero direction (shared origin: test value = sc,
-      // positive unless the origin is inside the sphere) / far-away origin (general: d2 huge)
-      a[q][0] = a[q][1] = a[q][2] = PRIMARY ? 0.f : -3.0e18f;
+      // idle slots must never look like candidates: zero vectors (shared origin: test value = sc,
+      // positive unless the origin is inside the sphere; general: a = -ku huge, d2 huge)
+      a[q][0] = a[q][1] = a[q][2] = 0.f;
       b[q][0] = b[q][1] = b[q][2] = 0.f;
+      nku[q] = 3.0e18f; nkv[q] = 0.f;
       if (active[q]) {
         my_nodes++;
         if (PRIMARY) {
@@ -471,31 +481,39 @@ wf_trace_kernel(const __grid_constant__ WfParams P, int level) {
           a[q][0] = -(float)ray[0]; a[q][1] = -(float)ray[1]; a[q][2] = -(float)ray[2];
         } else {
           const float4 ro = P.b.ray_o[node], rd = P.b.ray_d[node];
-          a[q][0] = -ro.x; a[q][1] = -ro.y; a[q][2] = -ro.z;
-          b[q][0] = ro.w; b[q][1] = rd.x; b[q][2] = rd.y;
+          const float dx = ro.w, dy = rd.x, dz = rd.y;
+          // branchless orthonormal basis (Duff et al. 2017): u, v unit, u.v = u.d = v.d = 0 to ~1 ulp
+          const float sg = copysignf(1.f, dz);
+          const float ka = -1.f / (sg + dz);
+          const float kb = dx * dy * ka;
+          a[q][0] = 1.f + sg * dx * dx * ka; a[q][1] = sg * kb; a[q][2] = -sg * dx;
+          b[q][0] = kb; b[q][1] = sg + dy * dy * ka; b[q][2] = -dy;
+          nku[q] = -(a[q][0] * ro.x + a[q][1] * ro.y + a[q][2] * ro.z);
+          nkv[q] = -(b[q][0] * ro.x + b[q][1] * ro.y + b[q][2] * ro.z);
         }
       }
     }
     if (PRIMARY) sweep_primary<R>(tab, P.primary_x, n_pad, a, active, best, eps);
-    else sweep_general<R>(tab, P.geom, n_pad, a, b, active, best, eps);
+    else sweep_general<R>(tab, P.geom, P.b.ray_o, P.b.ray_d, n_pad, a, b, nku, nkv, nodes, active, best, eps);
     __syncwarp();
 #pragma unroll
     for (int q = 0; q < R; q++) {
       WfRay r;
-      r.node = (uint32_t)base + (uint32_t)q * 32u + lane;
+      r.node = nodes[q];
       r.active = active[q];
       r.path = 1; r.pixsub = r.node; r.segs_left = P.fr64.segs;
-      if (PRIMARY) {
-        r.o[0] = P.origin[0]; r.o[1] = P.origin[1]; r.o[2] = P.origin[2];
-        r.d[0] = -a[q][0]; r.d[1] = -a[q][1]; r.d[2] = -a[q][2];
-      } else {
-        r.o[0] = -a[q][0]; r.o[1] = -a[q][1]; r.o[2] = -a[q][2];
-        r.d[0] = b[q][0]; r.d[1] = b[q][1]; r.d[2] = b[q][2];
+      r.o[0] = P.origin[0]; r.o[1] = P.origin[1]; r.o[2] = P.origin[2];
+      r.d[0] = -a[q][0]; r.d[1] = -a[q][1]; r.d[2] = -a[q][2];
+      if (!PRIMARY) {
+        r.d[0] = r.d[1] = r.d[2] = 0.f;
         if (r.active) {
+          const float4 ro = P.b.ray_o[r.node], rd = P.b.ray_d[r.node];
           const int2 lk = P.b.link[r.node];
+          r.o[0] = ro.x; r.o[1] = ro.y; r.o[2] = ro.z;
+          r.d[0] = ro.w; r.d[1] = rd.x; r.d[2] = rd.y;
           r.path = (uint32_t)lk.y & 0xffffffu;
           r.segs_left = (int)((uint32_t)lk.y >> 24);
-          r.pixsub = __float_as_uint(P.b.ray_d[r.node].w);   // pixel*spp+sub of the level-1 ancestor
+          r.pixsub = __float_as_uint(rd.w);                  // pixel*spp+sub of the level-1 ancestor
         }
       }
       process_hit(P, r, best[q], lane);
@@ -582,7 +600,10 @@ wf_shadow_kernel(const __grid_constant__ WfParams P, int k) {
       if (any & 0xffu) {
 #pragma unroll
         for (int q = 0; q < R; q++) {
-          const uint32_t m = mask[q] & 0xffu;
+          uint32_t m = mask[q] & 0xffu;
+          // the ray ends ON sphere hit_i, so that sphere is always a candidate; drop its bit here
+          // (main.js:294 skips it) instead of paying a divergent slow-path call to find that out
+          if (j == (hit_i[q] & ~(WF_GROUP - 1))) m &= ~(0x80u >> (hit_i[q] & (WF_GROUP - 1)));
           if (m && I[q] != 0.f) {
             I[q] = slow_shadow(exact, P.sc.mtl, j, m, nw[q][0], nw[q][1], nw[q][2], len[q], hit_i[q], eps, I[q]);
             if (I[q] == 0.f) nw[q][0] = nw[q][1] = nw[q][2] = 0.f;   // fully occluded: stop testing
