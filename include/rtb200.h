@@ -59,7 +59,7 @@ enum {
   RTB_PRECISION_FP64 = 1    /* validation kernel, reference operation order, no FMA contraction  */
 };
 enum {
-  RTB_KERNEL_AUTO = 0,      /* fp64 -> per-pixel kernel; fp32 -> wavefront                       */
+  RTB_KERNEL_AUTO = 0,      /* fp64, or fp32 with <= 32 spheres -> per-pixel kernel; else wavefront */
   RTB_KERNEL_PIXEL = 1,     /* one thread per pixel, explicit post-order stack                   */
   RTB_KERNEL_WAVEFRONT = 2  /* fp32 only: ballot-compacted ray queues per recursion level        */
 };
