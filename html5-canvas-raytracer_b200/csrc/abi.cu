@@ -167,7 +167,18 @@ DevFrameT<T> make_frame(const RtbCamera* cam, const RtbRenderOpts* o) {
 // Launch the kernels of one frame into d_out on stream st.  Synchronises only on the wavefront path
 // (queue-overflow check) or when counters are wanted.
 int render_to_device(RtbScene_* s, const RtbCamera* cam, const RtbRenderOpts* o, uint8_t* d_out,
-                     cudaStream_t st, RtbStats* stats) {
+                     cudaStream_t st, RtbStats* stats, bool async = false) {
+  // an asynchronous frame may still be in flight (shared workspace): collect it first; if it was THIS
+  // scene's and it overflowed, the caller has not been told yet that that frame is invalid
+  int prc = rtb_finish_pending();
+  if (prc != RTB_OK) return prc;
+  if (s->deferred_status != RTB_OK) {
+    const int d = s->deferred_status;
+    s->deferred_status = RTB_OK;
+    rtb_set_error("the previous asynchronous frame overflowed its ray queues and is invalid; the band size "
+                  "has been reduced - render it again (rtb_finish reports this per frame)");
+    return d;
+  }
   const RowMap rm = make_rowmap(cam, o);
   int kernel = o->kernel;
   // AUTO: the fused per-pixel kernel wins while a sweep is a handful of spheres (demo scene, N = 14:
@@ -180,7 +191,7 @@ int render_to_device(RtbScene_* s, const RtbCamera* cam, const RtbRenderOpts* o,
   uint32_t launches = 0;
   if (kernel == RTB_KERNEL_WAVEFRONT) {
     const DevFrameT<float> fr = make_frame<float>(cam, o);
-    return wf_render(s, cam, fr, rm, d_out, st, stats, stats != nullptr);
+    return wf_render(s, cam, fr, rm, d_out, st, stats, async);
   }
   unsigned long long* ctr = stats ? g_rtb.d_counters : nullptr;
   if (ctr) RTB_CUDA(cudaMemsetAsync(ctr, 0, 3 * sizeof(unsigned long long), st));
@@ -312,6 +323,7 @@ int rtb_init(int device) {
     RTB_CUDA(cudaEventCreateWithFlags(&g_rtb.copy_done[i], cudaEventDisableTiming));
   }
   RTB_CUDA(cudaMalloc(&g_rtb.d_counters, 3 * sizeof(unsigned long long)));
+  RTB_CUDA(cudaEventCreateWithFlags(&g_rtb.ev_async, cudaEventDisableTiming));
   g_rtb.inited = true;
   return RTB_OK;
 }
@@ -328,6 +340,8 @@ void rtb_shutdown(void) {
   cudaFree(g_rtb.d_frame[0]); cudaFree(g_rtb.d_frame[1]); cudaFree(g_rtb.d_counters);
   cudaFree(g_rtb.cached_arena);
   if (g_rtb.h_stage) cudaFreeHost(g_rtb.h_stage);
+  if (g_rtb.h_sticky) cudaFreeHost(g_rtb.h_sticky);
+  if (g_rtb.ev_async) cudaEventDestroy(g_rtb.ev_async);
   wf_free();
   (void)cudaGetLastError();
   g_rtb = RtbGlobal{};
@@ -439,6 +453,7 @@ int rtb_scene_create(const RtbSceneDesc* d, rtb_scene_t* out) {
 
 void rtb_scene_destroy(rtb_scene_t s) {
   if (!s) return;
+  if (g_rtb.pending_scene == s) (void)rtb_finish_pending();
   if (s->arena) {
     if (g_rtb.inited) {
       // renders are synchronous w.r.t. the host except rtb_render_device on a caller stream: drain
@@ -462,13 +477,26 @@ void rtb_scene_destroy(rtb_scene_t s) {
 
 uint64_t rtb_scene_h2d_bytes(rtb_scene_t s) { return s ? (uint64_t)s->h2d_bytes : 0; }
 
+int rtb_finish(rtb_scene_t s) {
+  if (!g_rtb.inited) { rtb_set_error("rtb_init() has not been called"); return RTB_ERR_NOT_INIT; }
+  if (!s) { rtb_set_error("NULL argument"); return RTB_ERR_INVALID; }
+  int rc = rtb_finish_pending();
+  if (rc != RTB_OK) return rc;
+  const int d = s->deferred_status;
+  s->deferred_status = RTB_OK;
+  if (d != RTB_OK)
+    rtb_set_error("the asynchronous frame overflowed its ray queues and is invalid; the band size has been "
+                  "reduced - issue the same render again");
+  return d;
+}
+
 int rtb_render_device(rtb_scene_t s, const RtbCamera* cam, const RtbRenderOpts* o, void* d_out,
                       void* cuda_stream, RtbStats* stats) {
   int rc = validate_render(s, cam, o, d_out);
   if (rc != RTB_OK) return rc;
   cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : g_rtb.stream;
   if (stats) { memset(stats, 0, sizeof *stats); RTB_CUDA(cudaEventRecord(g_rtb.ev0, st)); }
-  rc = render_to_device(s, cam, o, (uint8_t*)d_out, st, stats);
+  rc = render_to_device(s, cam, o, (uint8_t*)d_out, st, stats, /*async=*/stats == nullptr);
   if (rc != RTB_OK) return rc;
   if (stats) {
     RTB_CUDA(cudaEventRecord(g_rtb.ev1, st));

@@ -64,6 +64,11 @@ struct RtbScene_ {
   size_t h2d_bytes = 0;                   // bytes rtb_scene_create uploaded
   double primary_origin[3] = {0, 0, 0};
   bool primary_valid = false;
+  // asynchronous device renders (rtb_render_device without stats): the queue-overflow verdict of the
+  // last enqueued frame is collected by rtb_finish() / the next call on the library
+  int wf_rows_hint = 0;                   // band size known to fit (0 = none yet)
+  int pending_rows = 0;                   // band size of the frame in flight
+  int deferred_status = 0;                // RTB_OK or RTB_ERR_OVERFLOW, reported by rtb_finish()
 };
 
 struct RtbGlobal {
@@ -88,6 +93,9 @@ struct RtbGlobal {
   size_t cached_arena_bytes = 0;
   char* h_stage = nullptr;                    // pinned staging for scene uploads and per-camera tables
   size_t stage_bytes = 0;
+  void* h_sticky = nullptr;                   // pinned: per-call overflow flag + device counters
+  RtbScene_* pending_scene = nullptr;         // scene with an asynchronous frame in flight (at most one)
+  cudaEvent_t ev_async = nullptr;
   // per-kernel-class event pool for RtbStats.ms_* (only used when stats are requested)
   static const int kMaxTimers = 256;
   cudaEvent_t timers[kMaxTimers] = {};
@@ -170,6 +178,9 @@ inline void wf_make_geom_table(const RtbSphere* sp, int n, int n_pad, float4* ta
 }
 
 // wavefront pipeline: renders the rows of `rm` into d_out, splitting into bands as needed.
+// async = true: enqueue only; the overflow check is deferred to rtb_finish_pending().
 int wf_render(RtbScene_* s, const RtbCamera* cam, const DevFrameT<float>& fr, const RowMap& rm,
-              uint8_t* d_out, cudaStream_t st, RtbStats* stats, bool want_counts);
+              uint8_t* d_out, cudaStream_t st, RtbStats* stats, bool async);
+// Wait for the asynchronous frame in flight (if any) and file its verdict in its scene.
+int rtb_finish_pending();
 void wf_free();

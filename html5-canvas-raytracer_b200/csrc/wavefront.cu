@@ -432,23 +432,33 @@ __device__ __noinline__ void process_hit(const WfParams& P, const WfRay& r, unsi
 }
 
 // ---- TRACE ----------------------------------------------------------------------------------------------
-template <bool PRIMARY>
-__global__ void __launch_bounds__(WF_THREADS, WF_MIN_CTAS)
-wf_trace_kernel(const __grid_constant__ WfParams P, int level) {
-  constexpr int R = PRIMARY ? R_SHARED : R_GENERAL;
-  extern __shared__ float4 tab[];
-  const int n = P.sc.n_spheres, n_pad = P.n_pad;
-  {
-    const float4* src = PRIMARY ? P.primary_tab : P.geom_tab;
-    for (int i = threadIdx.x; i < n_pad; i += blockDim.x) tab[i] = src[i];
+// Rays per lane are a launch-time decision made on the device from the size of the level: R_SHARED /
+// R_GENERAL when the level fills the machine several times over, half or a quarter of that for small
+// levels (deep recursion levels, multi-GPU stripes), so that chunks stay plentiful and the tail short.
+// Cost model (SMSP cycles per sphere pair, measured with tools/sweep_micro*.cu): a pair costs
+// max(R * f, 32) per warp — f = FMA+ALU cycles per ray (9 shared-origin, 20 general), 32 = the two
+// broadcast LDS.128 when 16 warps share the SM's LSU — and a launch takes ceil(chunks / warps) rounds.
+RTB_DEVINL int pick_rays_per_lane(uint32_t count, int r_big, uint32_t f) {
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  int best_r = r_big;
+  uint64_t best_cost = ~0ull;
+#pragma unroll
+  for (int s = 0; s < 3; s++) {
+    const uint32_t r = (uint32_t)r_big >> s;
+    const uint32_t chunks = (count + 32u * r - 1u) / (32u * r);
+    const uint64_t rounds = (chunks + warps - 1u) / warps;
+    const uint64_t cost = rounds * (uint64_t)max(r * f, 32u);
+    if (cost < best_cost) { best_cost = cost; best_r = (int)r; }   // ties keep the larger R
   }
-  __syncthreads();
-  uint32_t begin, end;
-  level_range(P, level, begin, end);
-  const uint32_t lane = threadIdx.x & 31u;
+  return best_r;
+}
+
+template <bool PRIMARY, int R>
+RTB_DEVINL void trace_chunks(const WfParams& P, int level, const float4* __restrict__ tab, uint32_t begin,
+                             uint32_t end, uint32_t lane, unsigned long long& my_nodes) {
+  const int n_pad = P.n_pad;
   const float eps = P.sc.eps;
   const int W = P.fr64.width;
-  unsigned long long my_nodes = 0;
   constexpr uint32_t CHUNK = 32u * R;
 
   for (;;) {
@@ -519,6 +529,27 @@ wf_trace_kernel(const __grid_constant__ WfParams P, int level) {
       process_hit(P, r, best[q], lane);
     }
   }
+}
+
+template <bool PRIMARY>
+__global__ void __launch_bounds__(WF_THREADS, WF_MIN_CTAS)
+wf_trace_kernel(const __grid_constant__ WfParams P, int level) {
+  constexpr int RB = PRIMARY ? R_SHARED : R_GENERAL;
+  extern __shared__ float4 tab[];
+  const int n = P.sc.n_spheres, n_pad = P.n_pad;
+  {
+    const float4* src = PRIMARY ? P.primary_tab : P.geom_tab;
+    for (int i = threadIdx.x; i < n_pad; i += blockDim.x) tab[i] = src[i];
+  }
+  __syncthreads();
+  uint32_t begin, end;
+  level_range(P, level, begin, end);
+  const uint32_t lane = threadIdx.x & 31u;
+  unsigned long long my_nodes = 0;
+  const int r = pick_rays_per_lane(end - begin, RB, PRIMARY ? 9u : 20u);
+  if (r == RB) trace_chunks<PRIMARY, RB>(P, level, tab, begin, end, lane, my_nodes);
+  else if (r == RB / 2) trace_chunks<PRIMARY, RB / 2>(P, level, tab, begin, end, lane, my_nodes);
+  else trace_chunks<PRIMARY, RB / 4>(P, level, tab, begin, end, lane, my_nodes);
   // stats
   for (int o2 = 16; o2 > 0; o2 >>= 1) my_nodes += __shfl_down_sync(0xffffffffu, my_nodes, o2);
   if (lane == 0 && my_nodes) {
@@ -532,19 +563,13 @@ wf_trace_kernel(const __grid_constant__ WfParams P, int level) {
 // Occluder sweep of main.js:293-304 for light k, traced from the light toward hit.p.  Same fast test as
 // sweep_primary (table = C - light, sc); the slow path applies the reference's [0.001, light_len)
 // window along the reference's own ray (from hit.p toward the light): t = light_len - s.
-__global__ void __launch_bounds__(WF_THREADS, WF_MIN_CTAS)
-wf_shadow_kernel(const __grid_constant__ WfParams P, int k) {
-  constexpr int R = R_SHARED;
-  extern __shared__ float4 tab[];
+template <int R>
+RTB_DEVINL void shadow_chunks(const WfParams& P, int k, const float4* __restrict__ tab, uint32_t count,
+                              uint32_t lane, unsigned long long& my_rays, unsigned long long& my_tests) {
   const int n = P.sc.n_spheres, n_pad = P.n_pad;
-  for (int i = threadIdx.x; i < n_pad; i += blockDim.x) tab[i] = P.light_tab[k][i];
-  __syncthreads();
   const float4* __restrict__ exact = P.light_x[k];
-  const uint32_t count = *((volatile uint32_t*)&P.b.ctr->sq_count[k]);
-  const uint32_t lane = threadIdx.x & 31u;
   const float eps = P.sc.eps;
   const float lx = P.sc.lights[k][0], ly = P.sc.lights[k][1], lz = P.sc.lights[k][2];
-  unsigned long long my_rays = 0, my_tests = 0;
   constexpr uint32_t CHUNK = 32u * R;
 
   for (;;) {
@@ -641,6 +666,21 @@ wf_shadow_kernel(const __grid_constant__ WfParams P, int k) {
       }
     }
   }
+}
+
+__global__ void __launch_bounds__(WF_THREADS, WF_MIN_CTAS)
+wf_shadow_kernel(const __grid_constant__ WfParams P, int k) {
+  extern __shared__ float4 tab[];
+  const int n_pad = P.n_pad;
+  for (int i = threadIdx.x; i < n_pad; i += blockDim.x) tab[i] = P.light_tab[k][i];
+  __syncthreads();
+  const uint32_t count = *((volatile uint32_t*)&P.b.ctr->sq_count[k]);
+  const uint32_t lane = threadIdx.x & 31u;
+  unsigned long long my_rays = 0, my_tests = 0;
+  const int r = pick_rays_per_lane(count, R_SHARED, 9u);
+  if (r == R_SHARED) shadow_chunks<R_SHARED>(P, k, tab, count, lane, my_rays, my_tests);
+  else if (r == R_SHARED / 2) shadow_chunks<R_SHARED / 2>(P, k, tab, count, lane, my_rays, my_tests);
+  else shadow_chunks<R_SHARED / 4>(P, k, tab, count, lane, my_rays, my_tests);
   for (int o2 = 16; o2 > 0; o2 >>= 1) {
     my_rays += __shfl_down_sync(0xffffffffu, my_rays, o2);
     my_tests += __shfl_down_sync(0xffffffffu, my_tests, o2);
@@ -767,9 +807,27 @@ void wf_free() {
   g_rtb.wf_bytes = 0;
 }
 
+int rtb_finish_pending() {
+  RtbScene_* s = g_rtb.pending_scene;
+  if (!s) return RTB_OK;
+  g_rtb.pending_scene = nullptr;
+  RTB_CUDA(cudaEventSynchronize(g_rtb.ev_async));
+  const WfSticky& h = *static_cast<const WfSticky*>(g_rtb.h_sticky);
+  if (h.overflow) {
+    if (s->pending_rows <= 1) {
+      rtb_set_error("ray queues overflow even with one-row bands");
+      s->deferred_status = RTB_ERR_OVERFLOW;
+      return RTB_OK;
+    }
+    s->wf_rows_hint = std::max(1, s->pending_rows / 2);   // the same call will now use smaller bands
+    s->deferred_status = RTB_ERR_OVERFLOW;
+  }
+  return RTB_OK;
+}
+
 int wf_render(RtbScene_* s, const RtbCamera* cam, const DevFrameT<float>& fr32, const RowMap& rm,
-              uint8_t* d_out, cudaStream_t st, RtbStats* stats, bool want_counts) {
-  (void)want_counts;
+              uint8_t* d_out, cudaStream_t st, RtbStats* stats, bool async) {
+  if (stats) async = false;
   const int W = cam->width;
   const int n_rows = rm.n_local();
   if (n_rows <= 0) return RTB_OK;
@@ -857,7 +915,9 @@ int wf_render(RtbScene_* s, const RtbCamera* cam, const DevFrameT<float>& fr32, 
   const int grid_c = g_rtb.sm_count * 8;
 
   int rows_per_band = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)n_rows, (cap / 3) / sub_per_row));
-  WfSticky h_sticky;
+  if (s->wf_rows_hint > 0 && s->wf_rows_hint < rows_per_band) rows_per_band = s->wf_rows_hint;   // learnt earlier
+  if (!g_rtb.h_sticky) RTB_CUDA(cudaMallocHost(&g_rtb.h_sticky, sizeof(WfSticky)));
+  WfSticky& h_sticky = *static_cast<WfSticky*>(g_rtb.h_sticky);
   uint32_t launches = 0, bands = 0;
   // per-class timing (stats only): an event after every class of every band, classes tagged
   enum { T_START = 0, T_PRIMARY, T_SECONDARY, T_SHADOW, T_COMPOSE };
@@ -907,8 +967,14 @@ int wf_render(RtbScene_* s, const RtbCamera* cam, const DevFrameT<float>& fr32, 
       RTB_CUDA(cudaGetLastError());
     }
     RTB_CUDA(cudaMemcpyAsync(&h_sticky, P.sticky, sizeof h_sticky, cudaMemcpyDeviceToHost, st));
+    if (async) {                                          // verdict collected by rtb_finish_pending()
+      RTB_CUDA(cudaEventRecord(g_rtb.ev_async, st));
+      g_rtb.pending_scene = s;
+      s->pending_rows = rows_per_band;
+      return RTB_OK;
+    }
     RTB_CUDA(cudaStreamSynchronize(st));
-    if (!h_sticky.overflow) break;
+    if (!h_sticky.overflow) { if (attempt > 0) s->wf_rows_hint = rows_per_band; break; }
     if (rows_per_band == 1) {
       rtb_set_error("ray queues overflow even with one-row bands (cap_nodes=%llu, row=%llu sub-samples)",
                     (unsigned long long)cap, (unsigned long long)sub_per_row);

@@ -21,7 +21,7 @@ import numpy as np
 from . import _abi as A
 from .scene import make_opts
 
-DEFAULT_STRIPE_ROWS = 16
+DEFAULT_STRIPE_ROWS = 4     # 2160 rows / 4 = 540 stripes: per-rank row counts differ by < 1.5 % at 8 ranks
 
 
 # ---- partition arithmetic (mirrors RowMap in csrc/rtb_device.cuh; tested against it) ----------------
@@ -94,16 +94,26 @@ class StripedRenderer:
         import torch.distributed as dist
 
         stream = torch.cuda.current_stream().cuda_stream
-        if self.world <= 1:
-            self.r.redraw_device(camera, make_opts(**kw), self.frame.data_ptr(), stream, stats)
-            return self.frame
-        o = make_opts(stripe_rows=self.S, stripe_rank=self.rank, stripe_world=self.world, out_packed=1, **kw)
-        self.r.redraw_device(camera, o, self.local.data_ptr(), stream, stats)
-        # concatenated-along-dim-0 view: the form both NCCL and gloo accept
-        dist.all_gather_into_tensor(self.gathered.view(-1, self.W, 4), self.local)
-        A.check(self.lib.rtb_unstripe_device(self.gathered.data_ptr(), self.frame.data_ptr(), self.W, self.H,
-                                             self.S, self.world, stream))
-        return self.frame
+        # Everything below is only ENQUEUED (render, collective, de-interleave); the host then waits once
+        # in finish().  If a rank's ray queues overflowed, every rank repeats the frame (the collective
+        # must stay matched), which the deterministic band shrink makes succeed.
+        while True:
+            if self.world <= 1:
+                self.r.redraw_device(camera, make_opts(**kw), self.frame.data_ptr(), stream, stats)
+            else:
+                o = make_opts(stripe_rows=self.S, stripe_rank=self.rank, stripe_world=self.world, out_packed=1, **kw)
+                self.r.redraw_device(camera, o, self.local.data_ptr(), stream, stats)
+                # concatenated-along-dim-0 view: the form both NCCL and gloo accept
+                dist.all_gather_into_tensor(self.gathered.view(-1, self.W, 4), self.local)
+                A.check(self.lib.rtb_unstripe_device(self.gathered.data_ptr(), self.frame.data_ptr(), self.W,
+                                                     self.H, self.S, self.world, stream))
+            ok = self.r.finish()
+            if self.world > 1:
+                flag = torch.tensor([0 if ok else 1], dtype=torch.int32, device=self.frame.device)
+                dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+                ok = int(flag.item()) == 0
+            if ok:
+                return self.frame
 
 
 class FrameBatchRenderer:

@@ -77,6 +77,15 @@ class Renderer:
                                             C.c_void_p(stream) if stream else None,
                                             C.byref(stats) if stats is not None else None))
 
+    def finish(self) -> bool:
+        """Collect the verdict of the last asynchronous redraw_device().  True: the frame is valid.
+        False: its ray queues overflowed - the library has shrunk its bands; issue the same call again."""
+        rc = self._lib.rtb_finish(self._h)
+        if rc == A.RTB_ERR_OVERFLOW:
+            return False
+        A.check(rc)
+        return True
+
     def redraw_batch(self, cameras, out: Optional[np.ndarray] = None, stats: bool = False, opts=None, **kw):
         """Frame batch (orbit animation, BASELINE config 5): F x H x W x 4 uint8."""
         cams = [self._cam(c) for c in cameras]

@@ -186,10 +186,18 @@ int rtb_render(rtb_scene_t scene, const RtbCamera* cam, const RtbRenderOpts* opt
                uint8_t* out_rgba8, RtbStats* stats_or_null);
 
 /* Same, but `d_out_rgba8` is a DEVICE pointer on the library's device and `cuda_stream` is a
- * cudaStream_t (as void*, NULL = library stream).  Asynchronous w.r.t. the host unless stats are
- * requested.  Used by the multi-GPU host layer, which all-gathers stripes with NCCL. */
+ * cudaStream_t (as void*, NULL = library stream).  With stats == NULL the call only ENQUEUES the frame
+ * (no host synchronisation), so that the caller can queue its collective behind it; the one thing that
+ * can still go wrong afterwards - the ray queues of the wavefront path overflowing - is reported by
+ * rtb_finish().  Used by the multi-GPU host layer, which all-gathers stripes with NCCL. */
 int rtb_render_device(rtb_scene_t scene, const RtbCamera* cam, const RtbRenderOpts* opts,
                       void* d_out_rgba8, void* cuda_stream, RtbStats* stats_or_null);
+
+/* Wait for the scene's asynchronous frame (if any).  RTB_OK: the frame is valid.  RTB_ERR_OVERFLOW: its
+ * ray queues overflowed and the frame is INVALID; the library has already reduced the band size, so
+ * issuing the same rtb_render_device call again succeeds (deterministic).  A verdict that was never
+ * collected is returned by the next render call on the scene instead. */
+int rtb_finish(rtb_scene_t scene);
 
 /* Frame batch (config C5: orbit animation): nframes cameras, nframes*W*H*4 bytes out (host). */
 int rtb_render_batch(rtb_scene_t scene, const RtbCamera* cams, int32_t nframes,

@@ -241,3 +241,37 @@ def test_c3_full_size_sampled_rows(rt, oracle):
         s64 = lsb_stats(img64[rows], ref[rows])
         print("C3 4K fp64 on", len(rows), "rows:", s64)
         assert s64["within1"] >= FP64_WITHIN1 and s64["psnr"] >= FP64_PSNR_DB
+
+
+def test_async_device_render_reports_overflow_through_finish(rt, demo):
+    """rtb_render_device without stats only enqueues; a ray-queue overflow surfaces in rtb_finish(), the
+    library shrinks its bands, and repeating the same call converges to the identical frame."""
+    torch = pytest.importorskip("torch")
+    cam = rt.scenes.demo_camera(320, 200)
+    full = demo.redraw(cam, kernel=rt.RTB_KERNEL_WAVEFRONT)
+    dev = torch.zeros((200, 320, 4), dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    o = rt.make_opts(kernel=rt.RTB_KERNEL_WAVEFRONT)
+    r2 = rt.Renderer(rt.scenes.demo_objects())
+    os.environ["RTB_WF_CAP_NODES"] = str(320 * 12)
+    try:
+        tries = 0
+        while True:
+            r2.redraw_device(cam, o, dev.data_ptr())
+            tries += 1
+            if r2.finish():
+                break
+            assert tries < 24
+        assert tries > 1                                   # the first, optimistic band size did overflow
+        torch.cuda.synchronize()
+        assert np.array_equal(dev.cpu().numpy(), full)
+        # an uncollected verdict is not lost: the next call on the scene reports it
+        r3 = rt.Renderer(rt.scenes.demo_objects())
+        r3.redraw_device(cam, o, dev.data_ptr())
+        with pytest.raises(rt.RtbError) as e:
+            r3.redraw_device(cam, o, dev.data_ptr())
+        assert e.value.code == rt._abi.RTB_ERR_OVERFLOW
+        r3.close()
+    finally:
+        del os.environ["RTB_WF_CAP_NODES"]
+        r2.close()
