@@ -314,6 +314,9 @@ int rtb_init(int device) {
   snprintf(g_rtb.name, sizeof g_rtb.name, "%s", prop.name);
   RTB_CUDA(cudaStreamCreateWithFlags(&g_rtb.stream, cudaStreamNonBlocking));
   RTB_CUDA(cudaStreamCreateWithFlags(&g_rtb.copy_stream, cudaStreamNonBlocking));
+  RTB_CUDA(cudaStreamCreateWithFlags(&g_rtb.stream2, cudaStreamNonBlocking));
+  RTB_CUDA(cudaEventCreateWithFlags(&g_rtb.ev_primary, cudaEventDisableTiming));
+  RTB_CUDA(cudaEventCreateWithFlags(&g_rtb.ev_early, cudaEventDisableTiming));
   RTB_CUDA(cudaEventCreate(&g_rtb.ev0));
   RTB_CUDA(cudaEventCreate(&g_rtb.ev1));
   RTB_CUDA(cudaEventCreate(&g_rtb.ev2));
@@ -333,6 +336,8 @@ void rtb_shutdown(void) {
   cudaDeviceSynchronize();
   cudaStreamDestroy(g_rtb.stream);
   cudaStreamDestroy(g_rtb.copy_stream);
+  cudaStreamDestroy(g_rtb.stream2);
+  cudaEventDestroy(g_rtb.ev_primary); cudaEventDestroy(g_rtb.ev_early);
   cudaEventDestroy(g_rtb.ev0); cudaEventDestroy(g_rtb.ev1);
   cudaEventDestroy(g_rtb.ev2); cudaEventDestroy(g_rtb.ev3);
   for (int i = 0; i < 2; i++) { cudaEventDestroy(g_rtb.frame_done[i]); cudaEventDestroy(g_rtb.copy_done[i]); }

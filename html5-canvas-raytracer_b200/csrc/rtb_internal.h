@@ -19,6 +19,11 @@ struct WfCounters {          // one small device struct, zeroed per band
   uint32_t sq_count[RTB_MAX_LIGHTS];      // shadow queue fill per light
   uint32_t work_trace[RTB_MAX_SEGS + 2];   // next chunk of level L (persistent-kernel work counters)
   uint32_t work_shadow[RTB_MAX_LIGHTS];
+  uint32_t work_trace_tail[RTB_MAX_SEGS + 2];   // small-chunk tail phase of the same launches
+  uint32_t work_shadow_tail[RTB_MAX_LIGHTS];
+  uint32_t work_shadow_early_tail;
+  uint32_t work_shadow_early;              // chunks of the early (level-1) pass of light 0
+  uint32_t sq_snap0;                       // fill of shadow queue 0 when the primary trace finished
   unsigned long long stat_nodes, stat_shadow, stat_tests;
 };
 
@@ -78,7 +83,8 @@ struct RtbGlobal {
   int clock_khz = 0;
   size_t smem_optin = 0;
   char name[128] = {0};
-  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  cudaStream_t stream = nullptr, copy_stream = nullptr, stream2 = nullptr;
+  cudaEvent_t ev_primary = nullptr, ev_early = nullptr;   // cross-stream order of the overlapped shadow pass
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
   cudaEvent_t frame_done[2] = {nullptr, nullptr}, copy_done[2] = {nullptr, nullptr};
   // library-owned output staging + wavefront workspace, shared by all scenes (one render in flight

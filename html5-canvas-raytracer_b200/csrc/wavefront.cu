@@ -99,6 +99,7 @@ RTB_DEVINL void publish_level(const WfParams& P, int level) {
       const uint32_t room = P.b.cap_nodes - P.n_sub;
       if (nc > room) nc = room;
       P.b.ctr->level_end[level] = nc;
+      if (level == 1) P.b.ctr->sq_snap0 = atomicAdd(&P.b.ctr->sq_count[0], 0u);   // early shadow pass range
       P.b.ctr->blocks_done = 0;
       __threadfence();
     }
@@ -436,8 +437,9 @@ __device__ __noinline__ void process_hit(const WfParams& P, const WfRay& r, unsi
 // R_GENERAL when the level fills the machine several times over, half or a quarter of that for small
 // levels (deep recursion levels, multi-GPU stripes), so that chunks stay plentiful and the tail short.
 // Cost model (SMSP cycles per sphere pair, measured with tools/sweep_micro*.cu): a pair costs
-// max(R * f, 32) per warp — f = FMA+ALU cycles per ray (9 shared-origin, 20 general), 32 = the two
-// broadcast LDS.128 when 16 warps share the SM's LSU — and a launch takes ceil(chunks / warps) rounds.
+// c(R) = max(R * f, 32) + 4 per warp — f = FMA+ALU cycles per ray (9 shared-origin, 20 general), 32 = the
+// two broadcast LDS.128 when 16 warps share the SM's LSU — and with chunks pulled dynamically a launch
+// lasts about c(R) * (chunks / warps + 1): the work, plus one chunk of tail.
 RTB_DEVINL int pick_rays_per_lane(uint32_t count, int r_big, uint32_t f) {
   const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
   int best_r = r_big;
@@ -446,15 +448,25 @@ RTB_DEVINL int pick_rays_per_lane(uint32_t count, int r_big, uint32_t f) {
   for (int s = 0; s < 3; s++) {
     const uint32_t r = (uint32_t)r_big >> s;
     const uint32_t chunks = (count + 32u * r - 1u) / (32u * r);
-    const uint64_t rounds = (chunks + warps - 1u) / warps;
-    const uint64_t cost = rounds * (uint64_t)max(r * f, 32u);
+    const uint64_t cost = (uint64_t)(max(r * f, 32u) + 4u) * ((uint64_t)chunks + warps);
     if (cost < best_cost) { best_cost = cost; best_r = (int)r; }   // ties keep the larger R
   }
   return best_r;
 }
 
+// Guided scheduling: the last part of a level is cut into SMALL chunks (r_small rays per lane) so that
+// the tail of the launch is one small chunk, not one big one.  Returns how many rays to leave for that
+// tail phase (a multiple of the small chunk; 0 when the big chunks are already the smallest).
+RTB_DEVINL uint32_t tail_rays(uint32_t count, int r, int r_small) {
+  if (r <= r_small) return 0;
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  uint32_t t = min(count / 4u, warps * 16u * (uint32_t)r);        // about half a big chunk per warp
+  const uint32_t q = 32u * (uint32_t)r_small;
+  return (t / q) * q;
+}
+
 template <bool PRIMARY, int R>
-RTB_DEVINL void trace_chunks(const WfParams& P, int level, const float4* __restrict__ tab, uint32_t begin,
+RTB_DEVINL void trace_chunks(const WfParams& P, uint32_t* work, const float4* __restrict__ tab, uint32_t begin,
                              uint32_t end, uint32_t lane, unsigned long long& my_nodes) {
   const int n_pad = P.n_pad;
   const float eps = P.sc.eps;
@@ -462,7 +474,7 @@ RTB_DEVINL void trace_chunks(const WfParams& P, int level, const float4* __restr
   constexpr uint32_t CHUNK = 32u * R;
 
   for (;;) {
-    const uint64_t base = (uint64_t)begin + (uint64_t)next_chunk(&P.b.ctr->work_trace[level], lane) * CHUNK;
+    const uint64_t base = (uint64_t)begin + (uint64_t)next_chunk(work, lane) * CHUNK;
     if (base >= end) break;
     float a[R][3], b[R][3];          // PRIMARY: a = -dir;  general: a = u, b = v (basis completing dir)
     float nku[R], nkv[R];            // general: -(u.org), -(v.org)
@@ -547,9 +559,12 @@ wf_trace_kernel(const __grid_constant__ WfParams P, int level) {
   const uint32_t lane = threadIdx.x & 31u;
   unsigned long long my_nodes = 0;
   const int r = pick_rays_per_lane(end - begin, RB, PRIMARY ? 9u : 20u);
-  if (r == RB) trace_chunks<PRIMARY, RB>(P, level, tab, begin, end, lane, my_nodes);
-  else if (r == RB / 2) trace_chunks<PRIMARY, RB / 2>(P, level, tab, begin, end, lane, my_nodes);
-  else trace_chunks<PRIMARY, RB / 4>(P, level, tab, begin, end, lane, my_nodes);
+  const uint32_t split = end - tail_rays(end - begin, r, RB / 4);
+  uint32_t* wa = &P.b.ctr->work_trace[level];
+  if (r == RB) trace_chunks<PRIMARY, RB>(P, wa, tab, begin, split, lane, my_nodes);
+  else if (r == RB / 2) trace_chunks<PRIMARY, RB / 2>(P, wa, tab, begin, split, lane, my_nodes);
+  else trace_chunks<PRIMARY, RB / 4>(P, wa, tab, begin, split, lane, my_nodes);
+  if (split < end) trace_chunks<PRIMARY, RB / 4>(P, &P.b.ctr->work_trace_tail[level], tab, split, end, lane, my_nodes);
   // stats
   for (int o2 = 16; o2 > 0; o2 >>= 1) my_nodes += __shfl_down_sync(0xffffffffu, my_nodes, o2);
   if (lane == 0 && my_nodes) {
@@ -564,8 +579,9 @@ wf_trace_kernel(const __grid_constant__ WfParams P, int level) {
 // sweep_primary (table = C - light, sc); the slow path applies the reference's [0.001, light_len)
 // window along the reference's own ray (from hit.p toward the light): t = light_len - s.
 template <int R>
-RTB_DEVINL void shadow_chunks(const WfParams& P, int k, const float4* __restrict__ tab, uint32_t count,
-                              uint32_t lane, unsigned long long& my_rays, unsigned long long& my_tests) {
+RTB_DEVINL void shadow_chunks(const WfParams& P, int k, const float4* __restrict__ tab, uint32_t first,
+                              uint32_t count, uint32_t* work, uint32_t lane, unsigned long long& my_rays,
+                              unsigned long long& my_tests) {
   const int n = P.sc.n_spheres, n_pad = P.n_pad;
   const float4* __restrict__ exact = P.light_x[k];
   const float eps = P.sc.eps;
@@ -573,7 +589,7 @@ RTB_DEVINL void shadow_chunks(const WfParams& P, int k, const float4* __restrict
   constexpr uint32_t CHUNK = 32u * R;
 
   for (;;) {
-    const uint64_t base = (uint64_t)next_chunk(&P.b.ctr->work_shadow[k], lane) * CHUNK;
+    const uint64_t base = (uint64_t)first + (uint64_t)next_chunk(work, lane) * CHUNK;
     if (base >= count) break;
     uint32_t node[R];
     int hit_i[R];
@@ -669,18 +685,27 @@ RTB_DEVINL void shadow_chunks(const WfParams& P, int k, const float4* __restrict
 }
 
 __global__ void __launch_bounds__(WF_THREADS, WF_MIN_CTAS)
-wf_shadow_kernel(const __grid_constant__ WfParams P, int k) {
+// phase 0: everything queued for light k.  phase 1 (k = 0 only): the EARLY pass over the entries the
+// primary trace queued ([0, sq_snap0)), launched on a second stream so that it overlaps the secondary
+// trace levels and fills their tails.  phase 2 (k = 0): the rest, [sq_snap0, end).
+wf_shadow_kernel(const __grid_constant__ WfParams P, int k, int phase) {
   extern __shared__ float4 tab[];
   const int n_pad = P.n_pad;
   for (int i = threadIdx.x; i < n_pad; i += blockDim.x) tab[i] = P.light_tab[k][i];
   __syncthreads();
-  const uint32_t count = *((volatile uint32_t*)&P.b.ctr->sq_count[k]);
+  uint32_t first = 0, count = *((volatile uint32_t*)&P.b.ctr->sq_count[k]);
+  uint32_t* work = &P.b.ctr->work_shadow[k];
+  if (phase == 1) { count = *((volatile uint32_t*)&P.b.ctr->sq_snap0); work = &P.b.ctr->work_shadow_early; }
+  else if (phase == 2) first = *((volatile uint32_t*)&P.b.ctr->sq_snap0);
   const uint32_t lane = threadIdx.x & 31u;
   unsigned long long my_rays = 0, my_tests = 0;
-  const int r = pick_rays_per_lane(count, R_SHARED, 9u);
-  if (r == R_SHARED) shadow_chunks<R_SHARED>(P, k, tab, count, lane, my_rays, my_tests);
-  else if (r == R_SHARED / 2) shadow_chunks<R_SHARED / 2>(P, k, tab, count, lane, my_rays, my_tests);
-  else shadow_chunks<R_SHARED / 4>(P, k, tab, count, lane, my_rays, my_tests);
+  uint32_t* work_tail = (phase == 1) ? &P.b.ctr->work_shadow_early_tail : &P.b.ctr->work_shadow_tail[k];
+  const int r = pick_rays_per_lane(count - first, R_SHARED, 9u);
+  const uint32_t split = count - tail_rays(count - first, r, R_SHARED / 4);
+  if (r == R_SHARED) shadow_chunks<R_SHARED>(P, k, tab, first, split, work, lane, my_rays, my_tests);
+  else if (r == R_SHARED / 2) shadow_chunks<R_SHARED / 2>(P, k, tab, first, split, work, lane, my_rays, my_tests);
+  else shadow_chunks<R_SHARED / 4>(P, k, tab, first, split, work, lane, my_rays, my_tests);
+  if (split < count) shadow_chunks<R_SHARED / 4>(P, k, tab, split, count, work_tail, lane, my_rays, my_tests);
   for (int o2 = 16; o2 > 0; o2 >>= 1) {
     my_rays += __shfl_down_sync(0xffffffffu, my_rays, o2);
     my_tests += __shfl_down_sync(0xffffffffu, my_tests, o2);
@@ -947,13 +972,24 @@ int wf_render(RtbScene_* s, const RtbCamera* cam, const DevFrameT<float>& fr32, 
       wf_trace_kernel<true><<<grid_p, WF_THREADS, smem, st>>>(P, 1);
       launches++;
       if ((rc = mark(T_PRIMARY)) != RTB_OK) return rc;
+      // Without instrumentation the light-0 sweep of the level-1 nodes runs on a second stream,
+      // concurrently with the secondary trace levels (independent work; fills their tails).
+      const bool overlap = !stats && s->n_lights > 0 && fr32.segs > 1;
+      if (overlap) {
+        RTB_CUDA(cudaEventRecord(g_rtb.ev_primary, st));
+        RTB_CUDA(cudaStreamWaitEvent(g_rtb.stream2, g_rtb.ev_primary, 0));
+        wf_shadow_kernel<<<grid_l, WF_THREADS, smem, g_rtb.stream2>>>(P, 0, 1);
+        launches++;
+        RTB_CUDA(cudaEventRecord(g_rtb.ev_early, g_rtb.stream2));
+      }
       for (int L = 2; L <= fr32.segs; L++) {
         wf_trace_kernel<false><<<grid_s, WF_THREADS, smem, st>>>(P, L);
         launches++;
       }
       if ((rc = mark(T_SECONDARY)) != RTB_OK) return rc;
+      if (overlap) RTB_CUDA(cudaStreamWaitEvent(st, g_rtb.ev_early, 0));
       for (int k = 0; k < s->n_lights; k++) {
-        wf_shadow_kernel<<<grid_l, WF_THREADS, smem, st>>>(P, k);
+        wf_shadow_kernel<<<grid_l, WF_THREADS, smem, st>>>(P, k, (k == 0 && overlap) ? 2 : 0);
         launches++;
       }
       if ((rc = mark(T_SHADOW)) != RTB_OK) return rc;
