@@ -221,8 +221,9 @@ def main():
     st_acc = {"p": 0.0, "s": 0.0, "sh": 0.0, "c": 0.0, "k": 0.0, "launches": 0, "nodes": 0, "shadow": 0}
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    for _ in range(args.steps):
-        sr.redraw(cam, **opts_kw)            # the timed region carries no instrumentation
+    # K frames as a sequence: with N > 1 the render of frame i+1 overlaps the all-gather of frame i
+    # (StripedRenderer.redraw_sequence); every frame is fully assembled on every rank inside the region.
+    repeats = sr.redraw_sequence([cam] * args.steps, **opts_kw)   # the timed region carries no instrumentation
     ev1.record()
     barrier()
     ms_total = ev0.elapsed_time(ev1)

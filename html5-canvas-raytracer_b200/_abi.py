@@ -115,7 +115,7 @@ class RtbStats(C.Structure):
 
 # Every symbol include/rtb200.h declares; tests assert the built library exports all of them.
 EXPORTS = [
-    "rtb_init", "rtb_shutdown", "rtb_scene_create", "rtb_scene_destroy", "rtb_scene_h2d_bytes", "rtb_finish", "rtb_render",
+    "rtb_init", "rtb_shutdown", "rtb_scene_create", "rtb_scene_destroy", "rtb_scene_h2d_bytes", "rtb_finish", "rtb_copy_status_device", "rtb_render",
     "rtb_render_device", "rtb_render_batch", "rtb_unstripe_device", "rtb_stripe_local_rows",
     "rtb_stripe_padded_rows", "rtb_default_opts", "rtb_last_error", "rtb_version",
     "rtb_abi_version", "rtb_device_info",
@@ -150,13 +150,14 @@ def load() -> C.CDLL:
     lib.rtb_scene_destroy.argtypes = [vp]; lib.rtb_scene_destroy.restype = None
     lib.rtb_scene_h2d_bytes.argtypes = [vp]; lib.rtb_scene_h2d_bytes.restype = C.c_uint64
     lib.rtb_finish.argtypes = [vp]; lib.rtb_finish.restype = C.c_int
+    lib.rtb_copy_status_device.argtypes = [vp, vp, vp]; lib.rtb_copy_status_device.restype = C.c_int
     lib.rtb_render.argtypes = [vp, C.POINTER(RtbCamera), C.POINTER(RtbRenderOpts), vp, C.POINTER(RtbStats)]
     lib.rtb_render.restype = C.c_int
     lib.rtb_render_device.argtypes = [vp, C.POINTER(RtbCamera), C.POINTER(RtbRenderOpts), vp, vp, C.POINTER(RtbStats)]
     lib.rtb_render_device.restype = C.c_int
     lib.rtb_render_batch.argtypes = [vp, C.POINTER(RtbCamera), C.c_int32, C.POINTER(RtbRenderOpts), vp, C.POINTER(RtbStats)]
     lib.rtb_render_batch.restype = C.c_int
-    lib.rtb_unstripe_device.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]
+    lib.rtb_unstripe_device.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]
     lib.rtb_unstripe_device.restype = C.c_int
     lib.rtb_stripe_local_rows.argtypes = [C.c_int32] * 4; lib.rtb_stripe_local_rows.restype = C.c_int32
     lib.rtb_stripe_padded_rows.argtypes = [C.c_int32] * 3; lib.rtb_stripe_padded_rows.restype = C.c_int32
@@ -168,6 +169,16 @@ def load() -> C.CDLL:
     lib.rtb_device_info.restype = C.c_int
     _lib = lib
     return lib
+
+
+def stream_arg(stream):
+    """cudaStream_t argument of the device entry points.  None -> NULL = the library's own stream.  An
+    integer handle is passed through, except 0: that is CUDA's legacy default stream (what
+    torch.cuda.current_stream().cuda_stream returns outside a stream context) and must be named
+    explicitly as cudaStreamLegacy (0x1), because NULL already means "library stream"."""
+    if stream is None:
+        return None
+    return C.c_void_p(1 if int(stream) == 0 else int(stream))
 
 
 def check(code: int) -> None:

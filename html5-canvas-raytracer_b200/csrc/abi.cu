@@ -482,6 +482,20 @@ void rtb_scene_destroy(rtb_scene_t s) {
 
 uint64_t rtb_scene_h2d_bytes(rtb_scene_t s) { return s ? (uint64_t)s->h2d_bytes : 0; }
 
+int rtb_copy_status_device(rtb_scene_t s, void* d_dst, void* cuda_stream) {
+  if (!g_rtb.inited) { rtb_set_error("rtb_init() has not been called"); return RTB_ERR_NOT_INIT; }
+  if (!s || !d_dst) { rtb_set_error("NULL argument"); return RTB_ERR_INVALID; }
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : g_rtb.stream;
+  if (g_rtb.pending_scene == s && g_rtb.wf.ctr) {
+    // WfSticky.overflow is the first word after the per-band counter block
+    const char* flag = reinterpret_cast<const char*>(g_rtb.wf.ctr) + sizeof(WfCounters);
+    RTB_CUDA(cudaMemcpyAsync(d_dst, flag, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+  } else {
+    RTB_CUDA(cudaMemsetAsync(d_dst, 0, sizeof(uint32_t), st));     // nothing in flight that could overflow
+  }
+  return RTB_OK;
+}
+
 int rtb_finish(rtb_scene_t s) {
   if (!g_rtb.inited) { rtb_set_error("rtb_init() has not been called"); return RTB_ERR_NOT_INIT; }
   if (!s) { rtb_set_error("NULL argument"); return RTB_ERR_INVALID; }
@@ -603,14 +617,18 @@ int32_t rtb_stripe_padded_rows(int32_t height, int32_t stripe_rows, int32_t worl
 }
 
 int rtb_unstripe_device(const void* d_gathered, void* d_frame, int32_t width, int32_t height,
-                        int32_t stripe_rows, int32_t stripe_world, void* cuda_stream) {
+                        int32_t stripe_rows, int32_t stripe_world, int32_t rank_stride_rows, void* cuda_stream) {
   if (!g_rtb.inited) { rtb_set_error("rtb_init() has not been called"); return RTB_ERR_NOT_INIT; }
   if (!d_gathered || !d_frame || width <= 0 || height <= 0 || stripe_rows <= 0 || stripe_world < 1) {
     rtb_set_error("bad unstripe arguments");
     return RTB_ERR_INVALID;
   }
   cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : g_rtb.stream;
-  const int padded = rtb_stripe_padded_rows(height, stripe_rows, stripe_world);
+  int padded = rtb_stripe_padded_rows(height, stripe_rows, stripe_world);
+  if (rank_stride_rows != 0) {
+    if (rank_stride_rows < padded) { rtb_set_error("rank_stride_rows smaller than the padded stripe rows"); return RTB_ERR_INVALID; }
+    padded = rank_stride_rows;
+  }
   unstripe_kernel<<<g_rtb.sm_count * 8, 256, 0, st>>>((const uint32_t*)d_gathered, (uint32_t*)d_frame, width,
                                                      height, stripe_rows, stripe_world, padded);
   RTB_CUDA(cudaGetLastError());

@@ -71,7 +71,11 @@ def init_distributed(backend: str | None = None):
 
 
 class StripedRenderer:
-    """Row-stripe sharded redraw(): every rank ends up with the full framebuffer on its GPU."""
+    """Row-stripe sharded redraw(): every rank ends up with the full framebuffer on its GPU.
+
+    Gather layout per rank: [padded_rows + 1][W][4] — the packed stripe rows plus one trailer row whose
+    first word is the rank's status (non-zero: its ray queues overflowed, the frame must be repeated).
+    Shipping the status inside the payload gives every rank the same verdict from the one collective."""
 
     def __init__(self, renderer, width: int, height: int, rank: int, world: int,
                  stripe_rows: int = DEFAULT_STRIPE_ROWS):
@@ -82,38 +86,130 @@ class StripedRenderer:
         self.lib = A.load()
         self.n_local = self.lib.rtb_stripe_local_rows(height, stripe_rows, rank, world)
         self.padded = self.lib.rtb_stripe_padded_rows(height, stripe_rows, world)
+        self.stride = self.padded + 1
         dev = torch.device("cuda", torch.cuda.current_device())
+        self.dev = dev
         self.frame = torch.empty((height, width, 4), dtype=torch.uint8, device=dev)
         if world > 1:
-            self.local = torch.zeros((self.padded, width, 4), dtype=torch.uint8, device=dev)
-            self.gathered = torch.empty((world, self.padded, width, 4), dtype=torch.uint8, device=dev)
+            # two sets: frame i+1 renders while frame i is still being gathered (redraw_sequence)
+            self.local = [torch.zeros((self.stride, width, 4), dtype=torch.uint8, device=dev) for _ in range(2)]
+            self.gathered = [torch.empty((world, self.stride, width, 4), dtype=torch.uint8, device=dev) for _ in range(2)]
+            self.flags_host = torch.zeros((world,), dtype=torch.int32).pin_memory()
 
-    def redraw(self, camera, stats=None, **kw):
-        """Render this rank's stripes, all-gather, de-interleave.  Returns the device framebuffer."""
+    # -- building blocks ---------------------------------------------------------------------------
+    def _enqueue_render(self, camera, slot, stats, kw):
         import torch
-        import torch.distributed as dist
 
         stream = torch.cuda.current_stream().cuda_stream
-        # Everything below is only ENQUEUED (render, collective, de-interleave); the host then waits once
-        # in finish().  If a rank's ray queues overflowed, every rank repeats the frame (the collective
-        # must stay matched), which the deterministic band shrink makes succeed.
-        while True:
-            if self.world <= 1:
+        o = make_opts(stripe_rows=self.S, stripe_rank=self.rank, stripe_world=self.world, out_packed=1, **kw)
+        loc = self.local[slot]
+        self.r.redraw_device(camera, o, loc.data_ptr(), stream, stats)
+        A.check(self.lib.rtb_copy_status_device(self.r._h, loc[self.padded].data_ptr(), A.stream_arg(stream)))
+
+    def _enqueue_gather(self, slot):
+        import torch.distributed as dist
+
+        # concatenated-along-dim-0 view: the form both NCCL and gloo accept
+        return dist.all_gather_into_tensor(self.gathered[slot].view(-1, self.W, 4), self.local[slot], async_op=True)
+
+    def _enqueue_unstripe(self, slot):
+        import torch
+
+        stream = torch.cuda.current_stream().cuda_stream
+        A.check(self.lib.rtb_unstripe_device(self.gathered[slot].data_ptr(), self.frame.data_ptr(), self.W, self.H,
+                                             self.S, self.world, self.stride, A.stream_arg(stream)))
+        flags = self.gathered[slot][:, self.padded, 0, :].contiguous().view(torch.int32).view(-1)
+        self.flags_host.copy_(flags, non_blocking=True)
+
+    def _verdict(self) -> bool:
+        """Host-side: wait for the current stream, collect this rank's deferred status, read all flags."""
+        import torch
+
+        torch.cuda.current_stream().synchronize()
+        self.r.finish()                                   # clears the library's pending state (already complete)
+        return not bool(self.flags_host.any())
+
+    # -- one frame (latency mode) ----------------------------------------------------------------------
+    def redraw(self, camera, stats=None, **kw):
+        """Render this rank's stripes, all-gather, de-interleave.  Returns the device framebuffer.
+        Everything is only ENQUEUED; the host waits once.  If any rank's ray queues overflowed, every
+        rank sees that in the gathered status words and repeats the frame (the library has shrunk the
+        offending rank's bands, deterministically)."""
+        import torch
+
+        stream = torch.cuda.current_stream().cuda_stream
+        if self.world <= 1:
+            while True:
                 self.r.redraw_device(camera, make_opts(**kw), self.frame.data_ptr(), stream, stats)
-            else:
-                o = make_opts(stripe_rows=self.S, stripe_rank=self.rank, stripe_world=self.world, out_packed=1, **kw)
-                self.r.redraw_device(camera, o, self.local.data_ptr(), stream, stats)
-                # concatenated-along-dim-0 view: the form both NCCL and gloo accept
-                dist.all_gather_into_tensor(self.gathered.view(-1, self.W, 4), self.local)
-                A.check(self.lib.rtb_unstripe_device(self.gathered.data_ptr(), self.frame.data_ptr(), self.W,
-                                                     self.H, self.S, self.world, stream))
-            ok = self.r.finish()
-            if self.world > 1:
-                flag = torch.tensor([0 if ok else 1], dtype=torch.int32, device=self.frame.device)
-                dist.all_reduce(flag, op=dist.ReduceOp.MAX)
-                ok = int(flag.item()) == 0
-            if ok:
+                if self.r.finish():
+                    return self.frame
+        while True:
+            self._enqueue_render(camera, 0, stats, kw)
+            self._enqueue_gather(0).wait()
+            self._enqueue_unstripe(0)
+            if self._verdict():
                 return self.frame
+
+    # -- a sequence of frames (throughput mode) ----------------------------------------------------------
+    def redraw_sequence(self, cameras, on_frame=None, **kw):
+        """Software-pipelined: frame i+1 is rendered while frame i is in the collective.  `on_frame(i,
+        frame)` is called (device tensor, valid until the next call) once frame i is assembled.  Returns
+        the number of frames that had to be repeated because of queue overflows."""
+        import torch
+
+        stream = torch.cuda.current_stream().cuda_stream
+        n = len(cameras)
+        if self.world <= 1:
+            repeats = 0
+            for i, c in enumerate(cameras):
+                while True:
+                    self.r.redraw_device(c, make_opts(**kw), self.frame.data_ptr(), stream, None)
+                    if self.r.finish():
+                        break
+                    repeats += 1
+                if on_frame:
+                    on_frame(i, self.frame)
+            return repeats
+        repeats = 0
+        i = 0
+        work = None
+        while i < n or work is not None:
+            # enqueue the next render first so that it overlaps the collective of the previous frame
+            nxt = None
+            if i < n:
+                slot = i & 1
+                try:
+                    self._enqueue_render(cameras[i], slot, None, kw)
+                    nxt = (i, slot)
+                except A.RtbError as e:
+                    # enqueueing collected the verdict of the frame in flight: THIS rank overflowed on it.
+                    # Nothing was enqueued; fall through to that frame's status words so that every rank
+                    # restarts at the same frame.
+                    if e.code != A.RTB_ERR_OVERFLOW or work is None:
+                        raise
+            if work is not None:
+                (j, jslot), w = work
+                w.wait()
+                self._enqueue_unstripe(jslot)
+                ev = torch.cuda.Event()
+                ev.record()
+                ev.synchronize()                          # host waits for frame j only; frame i keeps the GPU busy
+                if bool(self.flags_host.any()):           # same words on every rank: same decision everywhere
+                    repeats += 1
+                    torch.cuda.current_stream().synchronize()
+                    self.r.finish()
+                    i, work = j, None                     # restart the pipeline at frame j
+                    continue
+                if on_frame:
+                    on_frame(j, self.frame)
+            if nxt is not None:
+                work = (nxt, self._enqueue_gather(nxt[1]))
+                i += 1
+            else:
+                work = None
+        torch.cuda.current_stream().synchronize()
+        self.r.finish()
+        return repeats
 
 
 class FrameBatchRenderer:

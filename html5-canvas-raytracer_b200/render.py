@@ -68,13 +68,14 @@ class Renderer:
         A.check(self._lib.rtb_render(self._h, C.byref(cam), C.byref(opts), C.c_void_p(host_ptr),
                                      C.byref(stats) if stats is not None else None))
 
-    def redraw_device(self, camera, opts, device_ptr: int, stream: int = 0,
+    def redraw_device(self, camera, opts, device_ptr: int, stream=None,
                       stats: Optional[A.RtbStats] = None) -> None:
         """Render into DEVICE memory (no D2H): `device_ptr` is a CUDA pointer on the library's device,
-        `stream` a cudaStream_t value (0 = the library's stream)."""
+        `stream` a cudaStream_t handle (None = the library's own stream; 0 = the legacy default stream,
+        e.g. torch.cuda.current_stream().cuda_stream)."""
         cam = self._cam(camera)
         A.check(self._lib.rtb_render_device(self._h, C.byref(cam), C.byref(opts), C.c_void_p(device_ptr),
-                                            C.c_void_p(stream) if stream else None,
+                                            A.stream_arg(stream),
                                             C.byref(stats) if stats is not None else None))
 
     def finish(self) -> bool:

@@ -199,14 +199,22 @@ int rtb_render_device(rtb_scene_t scene, const RtbCamera* cam, const RtbRenderOp
  * collected is returned by the next render call on the scene instead. */
 int rtb_finish(rtb_scene_t scene);
 
+/* Enqueue, on `cuda_stream`, a 4-byte device-to-device copy of the overflow flag of the frame just
+ * enqueued for `scene` (0 = valid, non-zero = ray queues overflowed) to `d_dst_u32`.  Lets a multi-GPU
+ * caller ship every rank's verdict inside the all-gather payload, so that all ranks take the same
+ * retry decision without a second collective. */
+int rtb_copy_status_device(rtb_scene_t scene, void* d_dst_u32, void* cuda_stream);
+
 /* Frame batch (config C5: orbit animation): nframes cameras, nframes*W*H*4 bytes out (host). */
 int rtb_render_batch(rtb_scene_t scene, const RtbCamera* cams, int32_t nframes,
                      const RtbRenderOpts* opts, uint8_t* out_rgba8, RtbStats* stats_or_null);
 
-/* De-interleave an all-gathered stripe buffer ([rank][local stripe rows][W*4]) into a row-major
- * framebuffer; both device pointers.  Used after ncclAllGather in the multi-GPU path. */
+/* De-interleave an all-gathered stripe buffer ([rank][rank_stride_rows][W*4]) into a row-major
+ * framebuffer; both device pointers.  Used after ncclAllGather in the multi-GPU path.
+ * rank_stride_rows = rows each rank contributes to the gather: 0 means rtb_stripe_padded_rows(); a larger
+ * value leaves room for trailer rows (the multi-GPU layer ships its status word in one). */
 int rtb_unstripe_device(const void* d_gathered, void* d_frame, int32_t width, int32_t height,
-                        int32_t stripe_rows, int32_t stripe_world, void* cuda_stream);
+                        int32_t stripe_rows, int32_t stripe_world, int32_t rank_stride_rows, void* cuda_stream);
 
 /* Number of rows rank `stripe_rank` owns / the padded per-rank row count used by the gather. */
 int32_t rtb_stripe_local_rows(int32_t height, int32_t stripe_rows, int32_t stripe_rank,

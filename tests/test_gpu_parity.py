@@ -179,7 +179,7 @@ def test_unstripe_device_roundtrip(rt, demo):
     for r in range(world):
         o = rt.make_opts(stripe_rows=S, stripe_rank=r, stripe_world=world, out_packed=1)
         demo.redraw_device(cam, o, gathered[r].data_ptr())
-    rt._abi.check(lib.rtb_unstripe_device(gathered.data_ptr(), frame.data_ptr(), 128, 70, S, world, None))
+    rt._abi.check(lib.rtb_unstripe_device(gathered.data_ptr(), frame.data_ptr(), 128, 70, S, world, 0, None))
     torch.cuda.synchronize()           # device-wide: drains the library stream too
     assert np.array_equal(frame.cpu().numpy(), full)
 
@@ -275,3 +275,21 @@ def test_async_device_render_reports_overflow_through_finish(rt, demo):
     finally:
         del os.environ["RTB_WF_CAP_NODES"]
         r2.close()
+
+
+def test_striped_renderer_single_rank_sequence(rt, synth):
+    """StripedRenderer at world = 1 (no collective): single frames and the sequence mode return the bytes
+    of a plain redraw; the multi-rank logic is covered by tests/test_multigpu_gloo.py and by the 2-GPU
+    bench."""
+    torch = pytest.importorskip("torch")
+    mg = __import__("importlib").import_module("html5-canvas-raytracer_b200.multigpu")
+    cam = rt.scenes.demo_camera(192, 108)
+    ref = synth.redraw(cam, segs=6)
+    sr = mg.StripedRenderer(synth, 192, 108, 0, 1)
+    f = sr.redraw(cam, segs=6)
+    torch.cuda.synchronize()
+    assert np.array_equal(f.cpu().numpy(), ref)
+    seen = []
+    rep = sr.redraw_sequence([cam, cam, cam], on_frame=lambda i, fr: seen.append((i, fr.cpu().numpy().copy())), segs=6)
+    assert rep == 0 and [i for i, _ in seen] == [0, 1, 2]
+    assert all(np.array_equal(a, ref) for _, a in seen)

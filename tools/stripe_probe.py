@@ -24,7 +24,7 @@ with rt.Renderer(objs) as r:
             torch.cuda.synchronize()
             wall = (time.perf_counter() - t0) * 100
             st = A.RtbStats()
-            r.redraw_device(cam, o, dev.data_ptr(), 0, st)
+            r.redraw_device(cam, o, dev.data_ptr(), None, st)
             res.append((rank, wall, st.kernel_ms, st.ms_trace_primary, st.ms_trace_secondary, st.ms_shadow, st.ms_compose, st.nodes))
         for x in res:
             print(f"world {world} rank {x[0]}: wall {x[1]:.3f} ms/frame  kernels {x[2]:.3f} (primary {x[3]:.3f} secondary {x[4]:.3f} shadow {x[5]:.3f} compose {x[6]:.3f}) nodes {x[7]}")
