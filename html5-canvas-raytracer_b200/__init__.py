@@ -14,7 +14,7 @@ library is not built or no GPU is visible (there is no CPU render path).
 from . import _abi
 from ._abi import (RTB_CAMERA_BASIS, RTB_CAMERA_REFERENCE, RTB_KERNEL_AUTO, RTB_KERNEL_PIXEL,
                    RTB_KERNEL_WAVEFRONT, RTB_PRECISION_FP32, RTB_PRECISION_FP64, RTB_STARS_HASH,
-                   RTB_STARS_OFF, RtbError)
+                   RTB_STARS_OFF, RTB_STARS_STREAM, RtbError)
 from .scene import (Camera, Material, SceneDesc, Sphere, Texture, checkerSampler, checkerTexture,
                     colorSampler, createMaterial, createSphere, createTexture, loadTexture, make_opts,
                     sortObjects, starSampler, textureFromRGBA, textureSampler)

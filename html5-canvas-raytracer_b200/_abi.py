@@ -20,7 +20,7 @@ RTB_ERR_NOT_INIT, RTB_ERR_OVERFLOW, RTB_ERR_UNSUPPORTED = -5, -6, -7
 RTB_SAMPLER_COLOR, RTB_SAMPLER_TEXTURE, RTB_SAMPLER_CHECKER, RTB_SAMPLER_STARS = 0, 1, 2, 3
 RTB_PRECISION_FP32, RTB_PRECISION_FP64 = 0, 1
 RTB_KERNEL_AUTO, RTB_KERNEL_PIXEL, RTB_KERNEL_WAVEFRONT = 0, 1, 2
-RTB_STARS_OFF, RTB_STARS_HASH = 0, 1
+RTB_STARS_OFF, RTB_STARS_HASH, RTB_STARS_STREAM = 0, 1, 2
 RTB_CAMERA_REFERENCE, RTB_CAMERA_BASIS = 0, 1
 
 D3 = C.c_double * 3
@@ -93,6 +93,8 @@ class RtbRenderOpts(C.Structure):
         ("stripe_world", C.c_int32),
         ("out_packed", C.c_int32),
         ("star_seed", C.c_uint64),
+        ("star_stream", C.POINTER(C.c_double)),
+        ("star_stream_len", C.c_uint64),
     ]
 
 

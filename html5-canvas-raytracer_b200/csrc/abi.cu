@@ -5,12 +5,18 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <new>
+#include <cub/device/device_scan.cuh>
 #include "rtb_internal.h"
 
 RtbGlobal g_rtb;
 static const int RTB_AUTO_PIXEL_MAX_SPHERES = 32;
 static thread_local char t_err[512] = "";
+// One render / scene operation at a time per process: the workspace, staging buffers and streams are
+// shared library state (the reference's caller is the single JS thread; this keeps other hosts safe).
+static std::recursive_mutex g_api_mutex;
+#define RTB_API_LOCK() std::lock_guard<std::recursive_mutex> api_lock_(g_api_mutex)
 
 void rtb_set_error(const char* fmt, ...) {
   va_list ap;
@@ -114,9 +120,18 @@ int validate_render(const RtbScene_* s, const RtbCamera* cam, const RtbRenderOpt
     rtb_set_error("the wavefront pipeline is fp32 only");
     return RTB_ERR_UNSUPPORTED;
   }
-  if (o->star_mode != RTB_STARS_OFF && o->star_mode != RTB_STARS_HASH) {
+  if (o->star_mode < RTB_STARS_OFF || o->star_mode > RTB_STARS_STREAM) {
     rtb_set_error("unknown star_mode %d", o->star_mode);
     return RTB_ERR_INVALID;
+  }
+  if (o->star_mode == RTB_STARS_STREAM) {
+    if (!o->star_stream || o->star_stream_len == 0) { rtb_set_error("RTB_STARS_STREAM needs star_stream"); return RTB_ERR_INVALID; }
+    const bool whole = o->y0 == 0 && (o->y1 <= 0 || o->y1 == cam->height) && o->stripe_world <= 1 && !o->out_packed;
+    if (!whole || o->kernel == RTB_KERNEL_WAVEFRONT || o->precision != RTB_PRECISION_FP64) {
+      rtb_set_error("RTB_STARS_STREAM replays the reference's call order: whole frames on the fp64 validation "
+                    "kernel only (one differing hit/miss in fp32 would shift every later stream index)");
+      return RTB_ERR_UNSUPPORTED;
+    }
   }
   if (cam->camera_mode != RTB_CAMERA_REFERENCE && cam->camera_mode != RTB_CAMERA_BASIS) {
     rtb_set_error("unknown camera_mode %d", cam->camera_mode);
@@ -186,7 +201,9 @@ int render_to_device(RtbScene_* s, const RtbCamera* cam, const RtbRenderOpts* o,
   // the wavefront wins as soon as the sweeps dominate (N = 1024 at 4K: 9.9 ms vs 200 ms).  Measured
   // crossover ~ 24-32 spheres.
   if (kernel == RTB_KERNEL_AUTO)
-    kernel = (o->precision == RTB_PRECISION_FP64 || s->n_spheres <= RTB_AUTO_PIXEL_MAX_SPHERES)
+    kernel = (o->precision == RTB_PRECISION_FP64 || s->n_spheres <= RTB_AUTO_PIXEL_MAX_SPHERES ||
+              o->star_mode == RTB_STARS_STREAM ||
+              (size_t)s->n_pad * sizeof(float4) > g_rtb.smem_optin)   // tables must fit shared memory
                  ? RTB_KERNEL_PIXEL : RTB_KERNEL_WAVEFRONT;
   uint32_t launches = 0;
   if (kernel == RTB_KERNEL_WAVEFRONT) {
@@ -196,11 +213,56 @@ int render_to_device(RtbScene_* s, const RtbCamera* cam, const RtbRenderOpts* o,
   unsigned long long* ctr = stats ? g_rtb.d_counters : nullptr;
   if (ctr) RTB_CUDA(cudaMemsetAsync(ctr, 0, 3 * sizeof(unsigned long long), st));
   int rc;
+  // RTB_STARS_STREAM: counting pass -> exclusive scan over pixels in raster order -> render pass
+  const double* d_stream = nullptr;
+  const unsigned long long* d_base = nullptr;
+  if (o->star_mode == RTB_STARS_STREAM) {
+    const size_t npx = (size_t)cam->width * cam->height;
+    size_t temp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, temp_bytes, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (int)npx, st);
+    const size_t need = o->star_stream_len * sizeof(double) + 2 * npx * sizeof(unsigned long long) + temp_bytes + 1024;
+    if (g_rtb.star_bytes < need) {
+      cudaFree(g_rtb.d_star);
+      g_rtb.d_star = nullptr; g_rtb.star_bytes = 0;
+      RTB_CUDA(cudaMalloc(&g_rtb.d_star, need));
+      g_rtb.star_bytes = need;
+    }
+    char* base = g_rtb.d_star;
+    unsigned long long* d_counts = reinterpret_cast<unsigned long long*>(base);
+    unsigned long long* d_b = d_counts + npx;
+    double* d_s = reinterpret_cast<double*>(d_b + npx);
+    void* d_temp = reinterpret_cast<char*>(d_s + o->star_stream_len) + ((256 - ((uintptr_t)(d_s + o->star_stream_len) & 255)) & 255);
+    RTB_CUDA(cudaMemcpyAsync(d_s, o->star_stream, o->star_stream_len * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (o->precision == RTB_PRECISION_FP64) {
+      DevFrameT<double> fr = make_frame<double>(cam, o);
+      fr.star_counts = d_counts;
+      rc = launch_pixel_f64(s->sc64, fr, rm, d_out, nullptr, st, &launches);
+    } else {
+      DevFrameT<float> fr = make_frame<float>(cam, o);
+      fr.star_counts = d_counts;
+      rc = launch_pixel_f32(s->sc32, fr, rm, d_out, nullptr, st, &launches);
+    }
+    if (rc != RTB_OK) return rc;
+    RTB_CUDA(cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, d_counts, d_b, (int)npx, st));
+    unsigned long long last[2];
+    RTB_CUDA(cudaMemcpyAsync(&last[0], d_counts + npx - 1, sizeof last[0], cudaMemcpyDeviceToHost, st));
+    RTB_CUDA(cudaMemcpyAsync(&last[1], d_b + npx - 1, sizeof last[1], cudaMemcpyDeviceToHost, st));
+    RTB_CUDA(cudaStreamSynchronize(st));
+    if (last[0] + last[1] > o->star_stream_len) {
+      rtb_set_error("star_stream holds %llu values but the frame draws %llu", (unsigned long long)o->star_stream_len,
+                    last[0] + last[1]);
+      return RTB_ERR_INVALID;
+    }
+    d_stream = d_s;
+    d_base = d_b;
+  }
   if (o->precision == RTB_PRECISION_FP64) {
-    const DevFrameT<double> fr = make_frame<double>(cam, o);
+    DevFrameT<double> fr = make_frame<double>(cam, o);
+    fr.star_stream = d_stream; fr.star_stream_len = o->star_stream_len; fr.star_base = d_base;
     rc = launch_pixel_f64(s->sc64, fr, rm, d_out, ctr, st, &launches);
   } else {
-    const DevFrameT<float> fr = make_frame<float>(cam, o);
+    DevFrameT<float> fr = make_frame<float>(cam, o);
+    fr.star_stream = d_stream; fr.star_stream_len = o->star_stream_len; fr.star_base = d_base;
     rc = launch_pixel_f32(s->sc32, fr, rm, d_out, ctr, st, &launches);
   }
   if (rc != RTB_OK) return rc;
@@ -287,6 +349,7 @@ __global__ void unstripe_kernel(const uint32_t* __restrict__ gathered, uint32_t*
 extern "C" {
 
 int rtb_init(int device) {
+  RTB_API_LOCK();
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
   if (e != cudaSuccess || count <= 0) {
@@ -332,6 +395,7 @@ int rtb_init(int device) {
 }
 
 void rtb_shutdown(void) {
+  RTB_API_LOCK();
   if (!g_rtb.inited) return;
   cudaDeviceSynchronize();
   cudaStreamDestroy(g_rtb.stream);
@@ -344,6 +408,7 @@ void rtb_shutdown(void) {
   for (int i = 0; i < g_rtb.n_timers; i++) cudaEventDestroy(g_rtb.timers[i]);
   cudaFree(g_rtb.d_frame[0]); cudaFree(g_rtb.d_frame[1]); cudaFree(g_rtb.d_counters);
   cudaFree(g_rtb.cached_arena);
+  cudaFree(g_rtb.d_star);
   if (g_rtb.h_stage) cudaFreeHost(g_rtb.h_stage);
   if (g_rtb.h_sticky) cudaFreeHost(g_rtb.h_sticky);
   if (g_rtb.ev_async) cudaEventDestroy(g_rtb.ev_async);
@@ -353,6 +418,7 @@ void rtb_shutdown(void) {
 }
 
 int rtb_scene_create(const RtbSceneDesc* d, rtb_scene_t* out) {
+  RTB_API_LOCK();
   if (!out) { rtb_set_error("out is NULL"); return RTB_ERR_INVALID; }
   *out = nullptr;
   if (!g_rtb.inited) { rtb_set_error("rtb_init() has not been called"); return RTB_ERR_NOT_INIT; }
@@ -457,6 +523,7 @@ int rtb_scene_create(const RtbSceneDesc* d, rtb_scene_t* out) {
 }
 
 void rtb_scene_destroy(rtb_scene_t s) {
+  RTB_API_LOCK();
   if (!s) return;
   if (g_rtb.pending_scene == s) (void)rtb_finish_pending();
   if (s->arena) {
@@ -483,6 +550,7 @@ void rtb_scene_destroy(rtb_scene_t s) {
 uint64_t rtb_scene_h2d_bytes(rtb_scene_t s) { return s ? (uint64_t)s->h2d_bytes : 0; }
 
 int rtb_copy_status_device(rtb_scene_t s, void* d_dst, void* cuda_stream) {
+  RTB_API_LOCK();
   if (!g_rtb.inited) { rtb_set_error("rtb_init() has not been called"); return RTB_ERR_NOT_INIT; }
   if (!s || !d_dst) { rtb_set_error("NULL argument"); return RTB_ERR_INVALID; }
   cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : g_rtb.stream;
@@ -497,6 +565,7 @@ int rtb_copy_status_device(rtb_scene_t s, void* d_dst, void* cuda_stream) {
 }
 
 int rtb_finish(rtb_scene_t s) {
+  RTB_API_LOCK();
   if (!g_rtb.inited) { rtb_set_error("rtb_init() has not been called"); return RTB_ERR_NOT_INIT; }
   if (!s) { rtb_set_error("NULL argument"); return RTB_ERR_INVALID; }
   int rc = rtb_finish_pending();
@@ -511,6 +580,7 @@ int rtb_finish(rtb_scene_t s) {
 
 int rtb_render_device(rtb_scene_t s, const RtbCamera* cam, const RtbRenderOpts* o, void* d_out,
                       void* cuda_stream, RtbStats* stats) {
+  RTB_API_LOCK();
   int rc = validate_render(s, cam, o, d_out);
   if (rc != RTB_OK) return rc;
   cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : g_rtb.stream;
@@ -528,6 +598,7 @@ int rtb_render_device(rtb_scene_t s, const RtbCamera* cam, const RtbRenderOpts* 
 }
 
 int rtb_render(rtb_scene_t s, const RtbCamera* cam, const RtbRenderOpts* o, uint8_t* out, RtbStats* stats) {
+  RTB_API_LOCK();
   int rc = validate_render(s, cam, o, out);
   if (rc != RTB_OK) return rc;
   const size_t bytes = (size_t)cam->width * cam->height * 4;
@@ -556,6 +627,7 @@ int rtb_render(rtb_scene_t s, const RtbCamera* cam, const RtbRenderOpts* o, uint
 
 int rtb_render_batch(rtb_scene_t s, const RtbCamera* cams, int32_t nframes, const RtbRenderOpts* o,
                      uint8_t* out, RtbStats* stats) {
+  RTB_API_LOCK();
   if (nframes < 0 || (nframes > 0 && !cams)) { rtb_set_error("bad frame batch"); return RTB_ERR_INVALID; }
   if (stats) memset(stats, 0, sizeof *stats);
   if (nframes == 0) return RTB_OK;
@@ -618,6 +690,7 @@ int32_t rtb_stripe_padded_rows(int32_t height, int32_t stripe_rows, int32_t worl
 
 int rtb_unstripe_device(const void* d_gathered, void* d_frame, int32_t width, int32_t height,
                         int32_t stripe_rows, int32_t stripe_world, int32_t rank_stride_rows, void* cuda_stream) {
+  RTB_API_LOCK();
   if (!g_rtb.inited) { rtb_set_error("rtb_init() has not been called"); return RTB_ERR_NOT_INIT; }
   if (!d_gathered || !d_frame || width <= 0 || height <= 0 || stripe_rows <= 0 || stripe_world < 1) {
     rtb_set_error("bad unstripe arguments");

@@ -100,7 +100,7 @@ RTB_DEVINL void shade_lights(const DevSceneT<T>& sc, const T* __restrict__ geom,
 template <typename T>
 __device__ void trace_tree(const DevSceneT<T>& sc, const T* __restrict__ geom, const DevFrameT<T>& fr,
                            const T org0[3], const T dir0[3], uint32_t px, uint32_t py, uint32_t sub,
-                           T out[3], PixelCounters& cnt) {
+                           T out[3], PixelCounters& cnt, unsigned long long star_base, uint32_t& star_k) {
   const T INF = Num<T>::inf();
   PixelFrame<T> stack[RTB_MAX_SEGS];
   int sp = -1;
@@ -211,7 +211,12 @@ __device__ void trace_tree(const DevSceneT<T>& sc, const T* __restrict__ geom, c
         const T rc[3] = {ret[0] * m.albedo[4], ret[1] * m.albedo[4], ret[2] * m.albedo[4]};
         T di, si, rgb[3];
         shade_lights<T>(sc, geom, m, f, di, si, cnt);
-        run_sampler<T>(sc, m, f.n, f.u, f.v, fr.star_mode, fr.star_seed, px, py, sub, f.node_id, rgb);
+        // the sampler runs AFTER both recursive calls (main.js:320): post-order, which is the order the
+        // reference consumes Math.random() in — star_k numbers this pixel's draws
+        unsigned long long star_idx = 0;
+        if (m.sampler_kind == RTB_SAMPLER_STARS) star_idx = star_base + (star_k++);
+        run_sampler<T>(sc, m, f.n, f.u, f.v, fr.star_mode, fr.star_seed, px, py, sub, f.node_id, rgb,
+                       fr.star_stream, star_idx, fr.star_stream_len);
         for (int c = 0; c < 3; c++) {                    // main.js:322-336
           const T shader = rgb[c] * di + rgb[c] * si + f.refl[c] + rc[c];
           ret[c] = js_max<T>(rgb[c] * m.albedo[0], js_min<T>(T(1), shader));
@@ -285,14 +290,18 @@ pixel_kernel(DevSceneT<T> sc, DevFrameT<T> fr, RowMap rm, uint8_t* __restrict__ 
     const int y = rm.local_to_y(lrow);
     const int g = fr.spp_grid;
     T acc[3] = {T(0), T(0), T(0)};
+    uint32_t star_k = 0;
+    const unsigned long long star_base = fr.star_base ? fr.star_base[(size_t)y * W + x] : 0ull;
     for (int j = 0; j < g; j++)
       for (int i = 0; i < g; i++) {
         T ray[3], rgb[3];
         primary_ray<T>(fr, x, y, i, j, ray);
-        trace_tree<T>(sc, geom, fr, fr.origin, ray, (uint32_t)x, (uint32_t)y, (uint32_t)(j * g + i), rgb, cnt);
+        trace_tree<T>(sc, geom, fr, fr.origin, ray, (uint32_t)x, (uint32_t)y, (uint32_t)(j * g + i), rgb, cnt,
+                      star_base, star_k);
         if (g == 1) { acc[0] = rgb[0]; acc[1] = rgb[1]; acc[2] = rgb[2]; }
         else { acc[0] += rgb[0]; acc[1] += rgb[1]; acc[2] += rgb[2]; }
       }
+    if (fr.star_counts) { fr.star_counts[(size_t)y * W + x] = star_k; continue; }   // counting pass: no pixel
     if (g > 1) { const T q = T(g * g); acc[0] /= q; acc[1] /= q; acc[2] /= q; }
     const uint32_t r8 = clamped_u8(T(255) * acc[0]), g8 = clamped_u8(T(255) * acc[1]),
                    b8 = clamped_u8(T(255) * acc[2]);

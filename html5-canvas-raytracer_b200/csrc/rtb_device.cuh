@@ -56,6 +56,13 @@ struct DevFrameT {
   int32_t y0, y1;                 // rows [y0,y1)
   int32_t stripe_rows, stripe_rank, stripe_world, out_packed;
   uint64_t star_seed;
+  // RTB_STARS_STREAM (pixel kernels only, whole frames): Math.random() values in the reference's call
+  // order.  Pass 1 counts the star-sampler calls of every pixel, an exclusive scan turns the counts into
+  // each pixel's first stream index, pass 2 renders.
+  const double* star_stream;              // device copy of the supplied stream
+  unsigned long long star_stream_len;
+  const unsigned long long* star_base;    // per pixel (y*W + x): index of its first draw      (pass 2)
+  unsigned long long* star_counts;        // per pixel: number of draws                        (pass 1)
   T origin[3], axisX[3], axisY[3], axisZ[3];
   T projW, projH, projD;
 };
@@ -170,7 +177,8 @@ RTB_DEVINL void sample_texture(const DevTexture& tx, const uchar4* __restrict__ 
 template <typename T>
 RTB_DEVINL void run_sampler(const DevSceneT<T>& sc, const DevMaterial<T>& m, const T n[3], T u, T v,
                             int star_mode, uint64_t star_seed, uint32_t px, uint32_t py, uint32_t sub,
-                            uint32_t node_id, T rgb[3]) {
+                            uint32_t node_id, T rgb[3], const double* star_stream = nullptr,
+                            unsigned long long star_idx = 0, unsigned long long star_len = 0) {
   switch (m.sampler_kind) {
     default:
     case RTB_SAMPLER_COLOR:                                   // main.js:404
@@ -191,6 +199,7 @@ RTB_DEVINL void run_sampler(const DevSceneT<T>& sc, const DevMaterial<T>& m, con
     case RTB_SAMPLER_STARS: {                                 // main.js:135-139
       T c = T(0.5);                                           // RTB_STARS_OFF: Math.random = () => 0.5
       if (star_mode == RTB_STARS_HASH) c = T(star_uniform(star_seed, px, py, sub, node_id));
+      else if (star_mode == RTB_STARS_STREAM && star_stream && star_idx < star_len) c = T(star_stream[star_idx]);
       if (c >= m.star_threshold) { rgb[0] = rgb[1] = rgb[2] = T(0); return; }
       c *= m.star_gain;
       rgb[0] = rgb[1] = rgb[2] = c;

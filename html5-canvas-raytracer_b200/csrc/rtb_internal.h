@@ -100,6 +100,8 @@ struct RtbGlobal {
   char* h_stage = nullptr;                    // pinned staging for scene uploads and per-camera tables
   size_t stage_bytes = 0;
   void* h_sticky = nullptr;                   // pinned: per-call overflow flag + device counters
+  char* d_star = nullptr;                     // RTB_STARS_STREAM scratch: counts, bases, stream, scan temp
+  size_t star_bytes = 0;
   RtbScene_* pending_scene = nullptr;         // scene with an asynchronous frame in flight (at most one)
   cudaEvent_t ev_async = nullptr;
   // per-kernel-class event pool for RtbStats.ms_* (only used when stats are requested)

@@ -304,11 +304,16 @@ class SceneDesc:
 
 def make_opts(segs=8, spp_grid=1, precision=A.RTB_PRECISION_FP32, kernel=A.RTB_KERNEL_AUTO,
               star_mode=A.RTB_STARS_OFF, y0=0, y1=0, stripe_rows=0, stripe_rank=0, stripe_world=0,
-              star_seed=0, out_packed=0) -> A.RtbRenderOpts:
+              star_seed=0, out_packed=0, star_stream=None) -> A.RtbRenderOpts:
     o = A.RtbRenderOpts()
     o.segs, o.spp_grid, o.precision, o.kernel, o.star_mode = segs, spp_grid, precision, kernel, star_mode
     o.y0, o.y1 = y0, y1
     o.stripe_rows, o.stripe_rank, o.stripe_world = stripe_rows, stripe_rank, stripe_world
     o.star_seed = star_seed
     o.out_packed = out_packed
+    if star_stream is not None:                        # RTB_STARS_STREAM: Math.random() values, call order
+        arr = np.ascontiguousarray(star_stream, np.float64)
+        o._keep_stream = arr                           # the C side reads the caller's memory during the call
+        o.star_stream = arr.ctypes.data_as(C.POINTER(C.c_double))
+        o.star_stream_len = arr.size
     return o

@@ -65,8 +65,13 @@ enum {
 };
 enum {
   RTB_STARS_OFF = 0,        /* Math.random() stubbed to a constant >= threshold: sky is black    */
-  RTB_STARS_HASH = 1        /* deterministic per-(pixel,node) counter hash in place of Math.random;
-                               NOT the reference's raster-order stream       */
+  RTB_STARS_HASH = 1,       /* deterministic per-(pixel,node) counter hash in place of Math.random;
+                               NOT the reference's raster-order stream                           */
+  RTB_STARS_STREAM = 2      /* exact replay: RtbRenderOpts.star_stream[n] is the value
+                               of the n-th Math.random() call in the reference's own call order (rows top
+                               to bottom, pixels left to right, post-order inside a pixel's tree).  Whole
+                               frames on the fp64 validation kernel only: the replay needs the exact
+                               ray tree (one differing hit/miss would shift every later index)     */
 };
 enum {
   RTB_CAMERA_REFERENCE = 0, /* main.js:187-191 verbatim: per-COMPONENT dist (bug-compatible)     */
@@ -144,6 +149,8 @@ typedef struct RtbRenderOpts {
                             untouched); 1: the rows this call renders are packed contiguously, in
                             ascending y, from the start of the buffer (the all-gather send layout) */
   uint64_t star_seed;    /* RTB_STARS_HASH seed                                                   */
+  const double* star_stream;   /* RTB_STARS_STREAM: host array of Math.random() values, caller-owned   */
+  uint64_t star_stream_len;    /* must cover every draw of the frame, else RTB_ERR_INVALID             */
 } RtbRenderOpts;
 
 /* Filled by every render call when non-NULL.  Device-side counts, not the oracle's. */

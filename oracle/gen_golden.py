@@ -46,9 +46,25 @@ def nf(fn, name="native"):
     return NativeFunction(lambda this, args: fn(this, args), name)
 
 
-def run_main_js(width, height, main_js_path=os.path.join(REFERENCE, "main.js"), verbose=False):
+def star_stream(n):
+    """Deterministic stand-in for the engine's Math.random() stream used by the `stars` golden frame:
+    value k = ((k * 2654435761) mod 2^32) / 2^32 * 0.004, i.e. uniform in [0, 0.004) so that a quarter of
+    the draws fall under main.js:137's 0.001 threshold and light a star."""
+    k = np.arange(n, dtype=np.uint64)
+    return ((k * np.uint64(2654435761)) % np.uint64(4294967296)).astype(np.float64) / 4294967296.0 * 0.004
+
+
+def run_main_js(width, height, main_js_path=os.path.join(REFERENCE, "main.js"), verbose=False, stars=False):
     png = importlib.import_module("html5-canvas-raytracer_b200.png")
-    it = Interpreter(random_fn=lambda: 0.5)
+    draws = [0]
+
+    def rnd():
+        if not stars:
+            return 0.5
+        k = draws[0]
+        draws[0] += 1
+        return ((k * 2654435761) % 4294967296) / 4294967296.0 * 0.004
+    it = Interpreter(random_fn=rnd)
     captured = {"put": 0, "text": None, "imagedata": None}
 
     def make_context(canvas):
@@ -136,6 +152,8 @@ def run_main_js(width, height, main_js_path=os.path.join(REFERENCE, "main.js"), 
         print(f"main.js {width}x{height}: {n} timer callbacks, {captured['put']} putImageData calls, "
               f"overlay {captured['text']!r}, {dt:.1f} s")
     assert captured["put"] == height, "spanish() must hand back one row per tick (main.js:200)"
+    if stars:
+        return rgba, captured["text"], draws[0]
     return rgba, captured["text"]
 
 
@@ -143,6 +161,15 @@ def main():
     sizes = [a for a in sys.argv[1:] if "x" in a] or ["64x36", "96x54"]
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
+    if "--stars" in sys.argv:
+        for s in sizes:
+            w, h = (int(v) for v in s.split("x"))
+            rgba, text, n = run_main_js(w, h, verbose=True, stars=True)
+            np.savez_compressed(os.path.join(out_dir, f"mainjs_demo_stars_{w}x{h}.npz"), rgba=rgba, n_draws=np.array(n),
+                                source=np.array("unmodified main.js build 741 under oracle/minijs, Math.random = "
+                                                "gen_golden.star_stream (k*2654435761 mod 2^32)/2^32*0.004"))
+            print("wrote", f"tests/golden/mainjs_demo_stars_{w}x{h}.npz", rgba.shape, "draws", n)
+        return
     for s in sizes:
         w, h = (int(v) for v in s.split("x"))
         rgba, text = run_main_js(w, h, verbose=True)

@@ -293,3 +293,34 @@ def test_striped_renderer_single_rank_sequence(rt, synth):
     rep = sr.redraw_sequence([cam, cam, cam], on_frame=lambda i, fr: seen.append((i, fr.cpu().numpy().copy())), segs=6)
     assert rep == 0 and [i for i, _ in seen] == [0, 1, 2]
     assert all(np.array_equal(a, ref) for _, a in seen)
+
+
+def test_star_stream_replay_matches_unmodified_main_js(rt, oracle, demo):
+    """RTB_STARS_STREAM: the fp64 kernel consumes a supplied Math.random() stream in the reference's own
+    call order (count pass -> raster-order scan -> render pass) and reproduces the framebuffer of the
+    UNMODIFIED main.js run with that stream (tests/golden/mainjs_demo_stars_96x54.npz) byte for byte."""
+    from oracle import gen_golden
+    golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mainjs_demo_stars_96x54.npz")
+    z = np.load(golden)
+    gold, n = z["rgba"], int(z["n_draws"])
+    stream = gen_golden.star_stream(n)
+    cam = rt.scenes.demo_camera(96, 54)
+    img64 = demo.redraw(cam, segs=8, precision=rt.RTB_PRECISION_FP64, star_mode=rt.RTB_STARS_STREAM, star_stream=stream)
+    assert np.array_equal(img64, gold)
+    # fp32 cannot replay a stream: one differing hit/miss shifts every later index -> refused
+    with pytest.raises(rt.RtbError) as e:
+        demo.redraw(cam, segs=8, precision=rt.RTB_PRECISION_FP32, star_mode=rt.RTB_STARS_STREAM, star_stream=stream)
+    assert e.value.code == rt._abi.RTB_ERR_UNSUPPORTED
+    # larger frame against the oracle fed with the same stream
+    cam2 = rt.scenes.demo_camera(320, 180)
+    big = gen_golden.star_stream(200000)
+    ref, cnt = oracle.render(demo.desc, cam2, rt.make_opts(segs=8), threads=1, rand_stream=big)
+    img = demo.redraw(cam2, segs=8, precision=rt.RTB_PRECISION_FP64, star_mode=rt.RTB_STARS_STREAM, star_stream=big)
+    assert np.array_equal(img, ref)
+    # a stream that is too short is refused, and so are partial frames / the wavefront path
+    with pytest.raises(rt.RtbError) as e:
+        demo.redraw(cam2, segs=8, precision=rt.RTB_PRECISION_FP64, star_mode=rt.RTB_STARS_STREAM, star_stream=big[:100])
+    assert e.value.code == rt._abi.RTB_ERR_INVALID and "draws" in str(e.value)
+    with pytest.raises(rt.RtbError) as e:
+        demo.redraw(cam2, precision=rt.RTB_PRECISION_FP64, star_mode=rt.RTB_STARS_STREAM, star_stream=big, y0=0, y1=10)
+    assert e.value.code == rt._abi.RTB_ERR_UNSUPPORTED

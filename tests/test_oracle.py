@@ -284,7 +284,8 @@ def test_oracle_matches_main_js_golden(rt, oracle):
     """tests/golden/mainjs_demo_*.npz: framebuffer of the UNMODIFIED /root/reference/main.js executed
     under oracle/minijs (gen_golden.py).  The C restatement must reproduce it (+-1 LSB allowance for
     libm vs the interpreter's Math, none expected)."""
-    files = sorted(f for f in os.listdir(GOLDEN) if f.startswith("mainjs_demo_") and f.endswith(".npz"))
+    files = sorted(f for f in os.listdir(GOLDEN)
+                   if f.startswith("mainjs_demo_") and f.endswith(".npz") and "stars" not in f)
     assert files, "golden frames missing: run oracle/gen_golden.py in the build container"
     sd = rt.SceneDesc(rt.scenes.demo_objects())
     for f in files:
@@ -294,3 +295,18 @@ def test_oracle_matches_main_js_golden(rt, oracle):
         img, _ = oracle.render(sd, rt.scenes.demo_camera(w, h), rt.make_opts(segs=8))
         s = lsb_stats(img, gold)
         assert s["within1"] == 1.0 and s["exact"] >= 0.9999, (f, s)
+
+
+def test_oracle_matches_main_js_golden_with_stars(rt, oracle):
+    """Math.random as an INPUT: main.js was run with a deterministic random stream
+    (gen_golden.star_stream); feeding the same stream to the restatement in the reference's call order
+    (raster order, post-order inside a pixel) reproduces the star field byte for byte."""
+    from oracle import gen_golden
+    z = np.load(os.path.join(GOLDEN, "mainjs_demo_stars_96x54.npz"))
+    gold, n = z["rgba"], int(z["n_draws"])
+    sd = rt.SceneDesc(rt.scenes.demo_objects())
+    img, cnt = oracle.render(sd, rt.scenes.demo_camera(96, 54), rt.make_opts(segs=8), threads=1,
+                             rand_stream=gen_golden.star_stream(n))
+    assert cnt["star_draws"] == n                       # one draw per tree node that hits the skybox
+    assert np.array_equal(img, gold)
+    assert (gold[:20, :, :3].max(axis=2) > 0).sum() > 100      # the stars are really there
