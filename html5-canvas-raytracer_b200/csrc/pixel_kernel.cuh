@@ -123,9 +123,20 @@ __device__ void trace_tree(const DevSceneT<T>& sc, const T* __restrict__ geom, c
         const uint32_t node_id = path;
         int hit_i = -1;                                  // main.js:223-230
         T best = INF, bt0 = T(0), bt1 = T(0);
+        // fp32 only: the sphere this ray starts on is evaluated analytically (roots {0, 2 tca}), as in
+        // wavefront.cu's slow_general — the float64 kernel keeps the reference's arithmetic untouched
+        const int self_i = (sizeof(T) == 4 && sp >= 0) ? stack[sp].hit_i : -1;
         for (int i = 0; i < n; i++) {
           T t0, t1;
-          const T t = intersect_sphere_t<T>(geom + 4 * i, org, dir, sc.eps, t0, t1);
+          T t;
+          if (i == self_i) {
+            const T* g = geom + 4 * i;
+            const T tca = dir[0] * (g[0] - org[0]) + dir[1] * (g[1] - org[1]) + dir[2] * (g[2] - org[2]);
+            t0 = T(0); t1 = T(2) * tca;
+            t = (t1 >= sc.eps) ? t1 : INF;
+          } else {
+            t = intersect_sphere_t<T>(geom + 4 * i, org, dir, sc.eps, t0, t1);
+          }
           if (t < best) { best = t; hit_i = i; bt0 = t0; bt1 = t1; }
         }
         cnt.sphere_tests += (unsigned long long)n;

@@ -154,7 +154,8 @@ __device__ __noinline__ unsigned long long slow_primary(const float4* __restrict
 __device__ __noinline__ unsigned long long slow_general(const float4* __restrict__ geom,
                                                         const float4* __restrict__ ray_o,
                                                         const float4* __restrict__ ray_d, int j, uint32_t m,
-                                                        uint32_t node, float eps, unsigned long long best) {
+                                                        uint32_t node, int self, float eps,
+                                                        unsigned long long best) {
   const float4 ro = ray_o[node], rd = ray_d[node];
   const float nox = -ro.x, noy = -ro.y, noz = -ro.z, dx = ro.w, dy = rd.x, dz = rd.y;
   while (m) {
@@ -164,6 +165,16 @@ __device__ __noinline__ unsigned long long slow_general(const float4* __restrict
     const float4 s = __ldg(geom + jj);
     const float L0 = s.x + nox, L1 = s.y + noy, L2 = s.z + noz;
     const float tca = dx * L0 + dy * L1 + dz * L2;
+    if (jj == self) {
+      // The ray starts ON this sphere (hit.p of its parent).  With p on the surface the roots of
+      // main.js:427-428 are exactly {0, 2 tca}: t0 < 0.001 always, so the hit is t1 = 2 tca when that
+      // clears the 0.001 window (the ray crosses the inside) and l is flipped.  The float64 reference
+      // computes precisely this (p is on the surface to 1e-15); in fp32 p sits up to ~5e-5 off the
+      // surface, and the generic formula then reports false grazing self-hits beyond the window.
+      const float t1 = 2.f * tca;
+      if (t1 >= eps) { const unsigned long long k = hit_key(t1, jj, true); if (k < best) best = k; }
+      continue;
+    }
     // d2 as |L - tca d|^2: no cancellation between |L|^2 and tca^2 for the r = 500 / 5000 spheres
     const float v0 = L0 - tca * dx, v1 = L1 - tca * dy, v2 = L2 - tca * dz;
     exact_update(tca, s.w - (v0 * v0 + v1 * v1 + v2 * v2), eps, jj, best);
@@ -242,8 +253,8 @@ template <int R>
 RTB_DEVINL void sweep_general(const float4* __restrict__ tab, const float4* __restrict__ geom,
                               const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, int n_pad,
                               const float (&u)[R][3], const float (&v)[R][3], const float (&nku)[R],
-                              const float (&nkv)[R], const uint32_t (&node)[R], const bool (&active)[R],
-                              unsigned long long (&best)[R], float eps) {
+                              const float (&nkv)[R], const uint32_t (&node)[R], const int (&self)[R],
+                              const bool (&active)[R], unsigned long long (&best)[R], float eps) {
   uint32_t mask[R];
 #pragma unroll
   for (int q = 0; q < R; q++) { best[q] = KEY_NONE; mask[q] = 0; }
@@ -271,7 +282,7 @@ RTB_DEVINL void sweep_general(const float4* __restrict__ tab, const float4* __re
 #pragma unroll
       for (int q = 0; q < R; q++) {
         const uint32_t m = mask[q] & 0xffu;
-        if (m && active[q]) best[q] = slow_general(geom, ray_o, ray_d, j, m, node[q], eps, best[q]);
+        if (m && active[q]) best[q] = slow_general(geom, ray_o, ray_d, j, m, node[q], self[q], eps, best[q]);
       }
     }
   }
@@ -479,6 +490,7 @@ RTB_DEVINL void trace_chunks(const WfParams& P, uint32_t* work, const float4* __
     float a[R][3], b[R][3];          // PRIMARY: a = -dir;  general: a = u, b = v (basis completing dir)
     float nku[R], nkv[R];            // general: -(u.org), -(v.org)
     uint32_t nodes[R];
+    int self[R];                     // general: sphere the ray starts on (hit_i of its parent node)
     bool active[R];
     unsigned long long best[R];
 #pragma unroll
@@ -491,6 +503,7 @@ RTB_DEVINL void trace_chunks(const WfParams& P, uint32_t* work, const float4* __
       a[q][0] = a[q][1] = a[q][2] = 0.f;
       b[q][0] = b[q][1] = b[q][2] = 0.f;
       nku[q] = 3.0e18f; nkv[q] = 0.f;
+      self[q] = -1;
       if (active[q]) {
         my_nodes++;
         if (PRIMARY) {
@@ -503,6 +516,7 @@ RTB_DEVINL void trace_chunks(const WfParams& P, uint32_t* work, const float4* __
           a[q][0] = -(float)ray[0]; a[q][1] = -(float)ray[1]; a[q][2] = -(float)ray[2];
         } else {
           const float4 ro = P.b.ray_o[node], rd = P.b.ray_d[node];
+          self[q] = __float_as_int(P.b.pos[P.b.link[node].x].w);
           const float dx = ro.w, dy = rd.x, dz = rd.y;
           // branchless orthonormal basis (Duff et al. 2017): u, v unit, u.v = u.d = v.d = 0 to ~1 ulp
           const float sg = copysignf(1.f, dz);
@@ -516,7 +530,7 @@ RTB_DEVINL void trace_chunks(const WfParams& P, uint32_t* work, const float4* __
       }
     }
     if (PRIMARY) sweep_primary<R>(tab, P.primary_x, n_pad, a, active, best, eps);
-    else sweep_general<R>(tab, P.geom, P.b.ray_o, P.b.ray_d, n_pad, a, b, nku, nkv, nodes, active, best, eps);
+    else sweep_general<R>(tab, P.geom, P.b.ray_o, P.b.ray_d, n_pad, a, b, nku, nkv, nodes, self, active, best, eps);
     __syncwarp();
 #pragma unroll
     for (int q = 0; q < R; q++) {
