@@ -170,6 +170,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--frames-in-flight", type=int, default=0,
+                    help="frames the sequence keeps in flight (0 = the host layer's default)")
     ap.add_argument("--config", default=CONFIG,
                     choices=["c3_synth1024_4k", "c2_demo_1080p_segs5", "c4_demo_4k_16spp"],
                     help="BASELINE.json config; the default (configs[2]) is the one the metric is quoted on")
@@ -213,8 +215,11 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident timing ------------------------------------------------------------------
+    fif = args.frames_in_flight or mg.DEFAULT_IN_FLIGHT
     for _ in range(args.warmup):
         sr.redraw(cam, **opts_kw)
+    # the sequence path too (its streams and one workspace per frame in flight are created on first use)
+    sr.redraw_sequence([cam] * max(args.warmup, fif + 1), frames_in_flight=fif, **opts_kw)
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -223,7 +228,7 @@ def main():
     ev0.record()
     # K frames as a sequence: with N > 1 the render of frame i+1 overlaps the all-gather of frame i
     # (StripedRenderer.redraw_sequence); every frame is fully assembled on every rank inside the region.
-    repeats = sr.redraw_sequence([cam] * args.steps, **opts_kw)   # the timed region carries no instrumentation
+    repeats = sr.redraw_sequence([cam] * args.steps, frames_in_flight=fif, **opts_kw)   # no instrumentation inside
     ev1.record()
     barrier()
     ms_total = ev0.elapsed_time(ev1)
@@ -352,6 +357,7 @@ def main():
                    "width": W, "height": H, "segs": segs, "spp": g * g, "n_spheres": cnt["n_spheres"],
                    "rays_per_frame": rays_per_frame, "kernel": "wavefront fp32" if use_wf else "per-pixel fp32 (AUTO, N <= 32)",
                    "partition": "single GPU" if world == 1 else f"interleaved {sr.S}-row stripes + NCCL all-gather",
+                   "frames_in_flight": fif,
                    "l2": "per-frame working set (ray/node queues, ~2.7 GB) exceeds the 126 MB L2; no flush needed"},
         "roofline": roofline,
         "e2e": {"value": round(e2e_value, 2), "unit": "Mrays/s", "ms_per_step": round(e2e_ms, 4),

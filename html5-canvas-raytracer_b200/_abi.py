@@ -117,7 +117,7 @@ class RtbStats(C.Structure):
 
 # Every symbol include/rtb200.h declares; tests assert the built library exports all of them.
 EXPORTS = [
-    "rtb_init", "rtb_shutdown", "rtb_scene_create", "rtb_scene_destroy", "rtb_scene_h2d_bytes", "rtb_finish", "rtb_copy_status_device", "rtb_render",
+    "rtb_init", "rtb_shutdown", "rtb_scene_create", "rtb_scene_destroy", "rtb_scene_h2d_bytes", "rtb_finish", "rtb_set_frames_in_flight", "rtb_copy_status_device", "rtb_render",
     "rtb_render_device", "rtb_render_batch", "rtb_unstripe_device", "rtb_stripe_local_rows",
     "rtb_stripe_padded_rows", "rtb_default_opts", "rtb_last_error", "rtb_version",
     "rtb_abi_version", "rtb_device_info",
@@ -152,6 +152,7 @@ def load() -> C.CDLL:
     lib.rtb_scene_destroy.argtypes = [vp]; lib.rtb_scene_destroy.restype = None
     lib.rtb_scene_h2d_bytes.argtypes = [vp]; lib.rtb_scene_h2d_bytes.restype = C.c_uint64
     lib.rtb_finish.argtypes = [vp]; lib.rtb_finish.restype = C.c_int
+    lib.rtb_set_frames_in_flight.argtypes = [C.c_int32]; lib.rtb_set_frames_in_flight.restype = C.c_int
     lib.rtb_copy_status_device.argtypes = [vp, vp, vp]; lib.rtb_copy_status_device.restype = C.c_int
     lib.rtb_render.argtypes = [vp, C.POINTER(RtbCamera), C.POINTER(RtbRenderOpts), vp, C.POINTER(RtbStats)]
     lib.rtb_render.restype = C.c_int

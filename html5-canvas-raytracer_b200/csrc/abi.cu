@@ -183,9 +183,16 @@ DevFrameT<T> make_frame(const RtbCamera* cam, const RtbRenderOpts* o) {
 // (queue-overflow check) or when counters are wanted.
 int render_to_device(RtbScene_* s, const RtbCamera* cam, const RtbRenderOpts* o, uint8_t* d_out,
                      cudaStream_t st, RtbStats* stats, bool async = false) {
-  // an asynchronous frame may still be in flight (shared workspace): collect it first; if it was THIS
-  // scene's and it overflowed, the caller has not been told yet that that frame is invalid
-  int prc = rtb_finish_pending();
+  // Asynchronous frames may still be in flight.  A synchronous call collects them all; an asynchronous
+  // one takes the next workspace slot and collects only the frame that used it last (with two frames in
+  // flight that is the frame before the previous one, which therefore keeps running).  If a collected
+  // frame was THIS scene's and overflowed, the caller has not been told yet that it is invalid.
+  int slot = 0;
+  if (async && !stats && g_rtb.frames_in_flight > 1) {
+    slot = g_rtb.next_slot % g_rtb.frames_in_flight;
+    g_rtb.next_slot = (slot + 1) % g_rtb.frames_in_flight;
+  }
+  int prc = rtb_finish_pending((async && !stats && g_rtb.frames_in_flight > 1) ? slot : -1);
   if (prc != RTB_OK) return prc;
   if (s->deferred_status != RTB_OK) {
     const int d = s->deferred_status;
@@ -208,7 +215,7 @@ int render_to_device(RtbScene_* s, const RtbCamera* cam, const RtbRenderOpts* o,
   uint32_t launches = 0;
   if (kernel == RTB_KERNEL_WAVEFRONT) {
     const DevFrameT<float> fr = make_frame<float>(cam, o);
-    return wf_render(s, cam, fr, rm, d_out, st, stats, async);
+    return wf_render(s, cam, fr, rm, d_out, st, stats, async, slot);
   }
   unsigned long long* ctr = stats ? g_rtb.d_counters : nullptr;
   if (ctr) RTB_CUDA(cudaMemsetAsync(ctr, 0, 3 * sizeof(unsigned long long), st));
@@ -377,9 +384,6 @@ int rtb_init(int device) {
   snprintf(g_rtb.name, sizeof g_rtb.name, "%s", prop.name);
   RTB_CUDA(cudaStreamCreateWithFlags(&g_rtb.stream, cudaStreamNonBlocking));
   RTB_CUDA(cudaStreamCreateWithFlags(&g_rtb.copy_stream, cudaStreamNonBlocking));
-  RTB_CUDA(cudaStreamCreateWithFlags(&g_rtb.stream2, cudaStreamNonBlocking));
-  RTB_CUDA(cudaEventCreateWithFlags(&g_rtb.ev_primary, cudaEventDisableTiming));
-  RTB_CUDA(cudaEventCreateWithFlags(&g_rtb.ev_early, cudaEventDisableTiming));
   RTB_CUDA(cudaEventCreate(&g_rtb.ev0));
   RTB_CUDA(cudaEventCreate(&g_rtb.ev1));
   RTB_CUDA(cudaEventCreate(&g_rtb.ev2));
@@ -389,7 +393,6 @@ int rtb_init(int device) {
     RTB_CUDA(cudaEventCreateWithFlags(&g_rtb.copy_done[i], cudaEventDisableTiming));
   }
   RTB_CUDA(cudaMalloc(&g_rtb.d_counters, 3 * sizeof(unsigned long long)));
-  RTB_CUDA(cudaEventCreateWithFlags(&g_rtb.ev_async, cudaEventDisableTiming));
   g_rtb.inited = true;
   return RTB_OK;
 }
@@ -400,8 +403,6 @@ void rtb_shutdown(void) {
   cudaDeviceSynchronize();
   cudaStreamDestroy(g_rtb.stream);
   cudaStreamDestroy(g_rtb.copy_stream);
-  cudaStreamDestroy(g_rtb.stream2);
-  cudaEventDestroy(g_rtb.ev_primary); cudaEventDestroy(g_rtb.ev_early);
   cudaEventDestroy(g_rtb.ev0); cudaEventDestroy(g_rtb.ev1);
   cudaEventDestroy(g_rtb.ev2); cudaEventDestroy(g_rtb.ev3);
   for (int i = 0; i < 2; i++) { cudaEventDestroy(g_rtb.frame_done[i]); cudaEventDestroy(g_rtb.copy_done[i]); }
@@ -410,8 +411,6 @@ void rtb_shutdown(void) {
   cudaFree(g_rtb.cached_arena);
   cudaFree(g_rtb.d_star);
   if (g_rtb.h_stage) cudaFreeHost(g_rtb.h_stage);
-  if (g_rtb.h_sticky) cudaFreeHost(g_rtb.h_sticky);
-  if (g_rtb.ev_async) cudaEventDestroy(g_rtb.ev_async);
   wf_free();
   (void)cudaGetLastError();
   g_rtb = RtbGlobal{};
@@ -460,7 +459,8 @@ int rtb_scene_create(const RtbSceneDesc* d, rtb_scene_t* out) {
   for (int k = 0; k < d->n_lights; k++) { o_ltab[k] = take(tb); o_lx[k] = take(tb); }
   const size_t o_gtab = take(tb);
   const size_t upload_bytes = off;                       // everything above is written by this call
-  const size_t o_ptab = take(tb), o_px = take(tb);       // primary tables: filled per camera
+  size_t o_ptab[RTB_MAX_IN_FLIGHT], o_px[RTB_MAX_IN_FLIGHT];   // primary tables: filled per camera, one set
+  for (int i = 0; i < RTB_MAX_IN_FLIGHT; i++) { o_ptab[i] = take(tb); o_px[i] = take(tb); }   // per frame in flight
   const size_t total = off;
 
   if (g_rtb.cached_arena && g_rtb.cached_arena_bytes >= total) {
@@ -513,8 +513,10 @@ int rtb_scene_create(const RtbSceneDesc* d, rtb_scene_t* out) {
     s->d_light_x[k] = reinterpret_cast<float4*>(ds + o_lx[k]);
   }
   s->d_geom_tab = reinterpret_cast<float4*>(ds + o_gtab);
-  s->d_primary_tab = reinterpret_cast<float4*>(ds + o_ptab);
-  s->d_primary_x = reinterpret_cast<float4*>(ds + o_px);
+  for (int i = 0; i < RTB_MAX_IN_FLIGHT; i++) {
+    s->d_primary_tab[i] = reinterpret_cast<float4*>(ds + o_ptab[i]);
+    s->d_primary_x[i] = reinterpret_cast<float4*>(ds + o_px[i]);
+  }
   fill_scene_view<double>(s->sc64, s, d, s->d_geom64, s->d_mtl64);
   fill_scene_view<float>(s->sc32, s, d, s->d_geom32, s->d_mtl32);
   guard.s = nullptr;
@@ -525,7 +527,8 @@ int rtb_scene_create(const RtbSceneDesc* d, rtb_scene_t* out) {
 void rtb_scene_destroy(rtb_scene_t s) {
   RTB_API_LOCK();
   if (!s) return;
-  if (g_rtb.pending_scene == s) (void)rtb_finish_pending();
+  for (int i = 0; i < RTB_MAX_IN_FLIGHT; i++)
+    if (g_rtb.slot[i].pending_scene == s) (void)rtb_finish_pending(i);
   if (s->arena) {
     if (g_rtb.inited) {
       // renders are synchronous w.r.t. the host except rtb_render_device on a caller stream: drain
@@ -554,9 +557,10 @@ int rtb_copy_status_device(rtb_scene_t s, void* d_dst, void* cuda_stream) {
   if (!g_rtb.inited) { rtb_set_error("rtb_init() has not been called"); return RTB_ERR_NOT_INIT; }
   if (!s || !d_dst) { rtb_set_error("NULL argument"); return RTB_ERR_INVALID; }
   cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : g_rtb.stream;
-  if (g_rtb.pending_scene == s && g_rtb.wf.ctr) {
+  const WfSlot& sl = g_rtb.slot[g_rtb.last_slot % RTB_MAX_IN_FLIGHT];   // the frame enqueued last
+  if (sl.pending_scene == s && sl.wf.ctr) {
     // WfSticky.overflow is the first word after the per-band counter block
-    const char* flag = reinterpret_cast<const char*>(g_rtb.wf.ctr) + sizeof(WfCounters);
+    const char* flag = reinterpret_cast<const char*>(sl.wf.ctr) + sizeof(WfCounters);
     RTB_CUDA(cudaMemcpyAsync(d_dst, flag, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
   } else {
     RTB_CUDA(cudaMemsetAsync(d_dst, 0, sizeof(uint32_t), st));     // nothing in flight that could overflow
@@ -564,11 +568,25 @@ int rtb_copy_status_device(rtb_scene_t s, void* d_dst, void* cuda_stream) {
   return RTB_OK;
 }
 
+int rtb_set_frames_in_flight(int n) {
+  RTB_API_LOCK();
+  if (!g_rtb.inited) { rtb_set_error("rtb_init() has not been called"); return RTB_ERR_NOT_INIT; }
+  if (n < 1 || n > RTB_MAX_IN_FLIGHT) {
+    rtb_set_error("frames in flight must be 1..%d (got %d)", RTB_MAX_IN_FLIGHT, n);
+    return RTB_ERR_INVALID;
+  }
+  int rc = rtb_finish_pending(-1);                         // statuses stay filed in their scenes
+  if (rc != RTB_OK) return rc;
+  g_rtb.frames_in_flight = n;
+  g_rtb.next_slot = 0;
+  return RTB_OK;
+}
+
 int rtb_finish(rtb_scene_t s) {
   RTB_API_LOCK();
   if (!g_rtb.inited) { rtb_set_error("rtb_init() has not been called"); return RTB_ERR_NOT_INIT; }
   if (!s) { rtb_set_error("NULL argument"); return RTB_ERR_INVALID; }
-  int rc = rtb_finish_pending();
+  int rc = rtb_finish_pending(-1);
   if (rc != RTB_OK) return rc;
   const int d = s->deferred_status;
   s->deferred_status = RTB_OK;

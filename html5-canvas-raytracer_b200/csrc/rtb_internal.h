@@ -43,6 +43,8 @@ struct WfBuffers {
   WfCounters* ctr;
 };
 
+constexpr int RTB_MAX_IN_FLIGHT = 4;   // workspace slots: asynchronous wavefront frames that may overlap
+
 struct RtbScene_ {
   int n_spheres = 0, n_textures = 0, n_lights = 0;
   std::vector<RtbSphere> spheres;         // host copy (primary table is camera dependent)
@@ -62,18 +64,34 @@ struct RtbScene_ {
   float4* d_geom_tab = nullptr;           // packed general-ray table (wf_make_geom_table)
   float4* d_light_tab[RTB_MAX_LIGHTS] = {nullptr, nullptr, nullptr, nullptr};   // packed, per light
   float4* d_light_x[RTB_MAX_LIGHTS] = {nullptr, nullptr, nullptr, nullptr};     // exact (L, c), per light
-  float4* d_primary_tab = nullptr;        // packed, per camera origin
-  float4* d_primary_x = nullptr;          // exact (L, c)
+  // per camera origin, one set per frame in flight (WfSlot): two frames of a moving camera may overlap
+  float4* d_primary_tab[RTB_MAX_IN_FLIGHT] = {};   // packed
+  float4* d_primary_x[RTB_MAX_IN_FLIGHT] = {};     // exact (L, c)
   char* arena = nullptr;                  // single device allocation all the pointers above point into
   size_t arena_bytes = 0;
   size_t h2d_bytes = 0;                   // bytes rtb_scene_create uploaded
-  double primary_origin[3] = {0, 0, 0};
-  bool primary_valid = false;
+  double primary_origin[RTB_MAX_IN_FLIGHT][3] = {};
+  bool primary_valid[RTB_MAX_IN_FLIGHT] = {};
   // asynchronous device renders (rtb_render_device without stats): the queue-overflow verdict of the
   // last enqueued frame is collected by rtb_finish() / the next call on the library
   int wf_rows_hint = 0;                   // band size known to fit (0 = none yet)
-  int pending_rows = 0;                   // band size of the frame in flight
   int deferred_status = 0;                // RTB_OK or RTB_ERR_OVERFLOW, reported by rtb_finish()
+};
+
+// Everything one wavefront frame in flight owns.  With rtb_set_frames_in_flight(n) consecutive
+// asynchronous device renders rotate through n slots, so that (issued on different streams) the kernels
+// of frame i+1 fill the tails of frame i's short per-level launches.
+struct WfSlot {
+  WfBuffers wf = {};
+  int wf_lights = 0;                          // shadow queues allocated
+  size_t wf_bytes = 0;
+  cudaStream_t stream2 = nullptr;             // overlapped early shadow pass
+  cudaEvent_t ev_primary = nullptr, ev_early = nullptr, ev_async = nullptr;
+  void* h_sticky = nullptr;                   // pinned: overflow flag + device counters of the last call
+  char* h_tab = nullptr;                      // pinned staging of the per-camera primary tables
+  size_t h_tab_bytes = 0;
+  RtbScene_* pending_scene = nullptr;         // scene with an asynchronous frame in flight in this slot
+  int pending_rows = 0;                       // band size of that frame
 };
 
 struct RtbGlobal {
@@ -83,27 +101,23 @@ struct RtbGlobal {
   int clock_khz = 0;
   size_t smem_optin = 0;
   char name[128] = {0};
-  cudaStream_t stream = nullptr, copy_stream = nullptr, stream2 = nullptr;
-  cudaEvent_t ev_primary = nullptr, ev_early = nullptr;   // cross-stream order of the overlapped shadow pass
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
   cudaEvent_t frame_done[2] = {nullptr, nullptr}, copy_done[2] = {nullptr, nullptr};
   // library-owned output staging + wavefront workspace, shared by all scenes (one render in flight
   // per process: the entry points serialise on a mutex), so creating a scene stays cheap
   uint8_t* d_frame[2] = {nullptr, nullptr};
   size_t frame_cap[2] = {0, 0};
-  WfBuffers wf = {};
-  int wf_lights = 0;                          // shadow queues allocated
-  size_t wf_bytes = 0;
+  WfSlot slot[RTB_MAX_IN_FLIGHT];
+  int frames_in_flight = 1;                   // 1 .. RTB_MAX_IN_FLIGHT (rtb_set_frames_in_flight)
+  int next_slot = 0, last_slot = 0;
   unsigned long long* d_counters = nullptr;   // 3 x u64 for the pixel kernels
   char* cached_arena = nullptr;               // last destroyed scene's device arena, reused by the next create
   size_t cached_arena_bytes = 0;
   char* h_stage = nullptr;                    // pinned staging for scene uploads and per-camera tables
   size_t stage_bytes = 0;
-  void* h_sticky = nullptr;                   // pinned: per-call overflow flag + device counters
   char* d_star = nullptr;                     // RTB_STARS_STREAM scratch: counts, bases, stream, scan temp
   size_t star_bytes = 0;
-  RtbScene_* pending_scene = nullptr;         // scene with an asynchronous frame in flight (at most one)
-  cudaEvent_t ev_async = nullptr;
   // per-kernel-class event pool for RtbStats.ms_* (only used when stats are requested)
   static const int kMaxTimers = 256;
   cudaEvent_t timers[kMaxTimers] = {};
@@ -188,7 +202,8 @@ inline void wf_make_geom_table(const RtbSphere* sp, int n, int n_pad, float4* ta
 // wavefront pipeline: renders the rows of `rm` into d_out, splitting into bands as needed.
 // async = true: enqueue only; the overflow check is deferred to rtb_finish_pending().
 int wf_render(RtbScene_* s, const RtbCamera* cam, const DevFrameT<float>& fr, const RowMap& rm,
-              uint8_t* d_out, cudaStream_t st, RtbStats* stats, bool async);
-// Wait for the asynchronous frame in flight (if any) and file its verdict in its scene.
-int rtb_finish_pending();
+              uint8_t* d_out, cudaStream_t st, RtbStats* stats, bool async, int slot);
+// Wait for the asynchronous frame in flight in `slot` (-1: in every slot, oldest first) and file its
+// verdict in its scene.
+int rtb_finish_pending(int slot);
 void wf_free();

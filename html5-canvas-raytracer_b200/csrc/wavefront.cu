@@ -64,6 +64,9 @@ struct WfParams {
   uint32_t n_sub;             // band_rows * W * spp  == number of level-1 nodes
   int32_t spp;                // g*g
   int32_t aligned4;           // W % 4 == 0 and output 16-byte aligned: uint4 stores
+  int32_t team_mode;          // 0 = whole-table chunks only, 1 = auto (team chunks for small levels and tails), 2 = team only
+  uint32_t team_rounds;       // auto: levels shorter than this many whole-table rounds run in team chunks throughout
+  int32_t fixed_r;            // 0: rays per lane from the cost model; 1/2/3: always R, R/2, R/4 and no guided tail
 };
 
 constexpr int WF_THREADS = 256;
@@ -77,6 +80,8 @@ static_assert(RTB_WF_GROUP % WF_GROUP == 0, "table padding must be a multiple of
 constexpr int R_SHARED = 8;              // rays per lane, shared-origin sweeps (primary, shadow)
 constexpr int R_GENERAL = 4;             // rays per lane, general sweep (reflect / refract rays)
 constexpr unsigned long long KEY_NONE = 0x7f800000ffffffffull;   // t = +inf, no sphere
+constexpr int R_TEAM = 4;                // rays per lane of a team chunk (see trace_team)
+constexpr int WF_WARPS = WF_THREADS / 32;
 
 RTB_DEVINL uint32_t lanemask_lt() { uint32_t m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
 
@@ -213,13 +218,13 @@ __device__ __noinline__ float slow_shadow(const float4* __restrict__ exact, cons
 // "the line hits the sphere and the sphere is ahead" (sc = sqrt(|L|^2 - r2), fp64 on the host, -inf
 // when the origin is inside).  3 FFMA2 per sphere pair per ray.
 template <int R>
-RTB_DEVINL void sweep_primary(const float4* __restrict__ tab, const float4* __restrict__ exact, int n_pad,
-                              const float (&nd)[R][3], const bool (&active)[R], unsigned long long (&best)[R],
-                              float eps) {
+RTB_DEVINL void sweep_primary(const float4* __restrict__ tab, const float4* __restrict__ exact, int j_begin,
+                              int j_end, const float (&nd)[R][3], const bool (&active)[R],
+                              unsigned long long (&best)[R], float eps) {
   uint32_t mask[R];
 #pragma unroll
   for (int q = 0; q < R; q++) { best[q] = KEY_NONE; mask[q] = 0; }
-  for (int j = 0; j < n_pad; j += WF_GROUP) {
+  for (int j = j_begin; j < j_end; j += WF_GROUP) {
 #pragma unroll
     for (int u = 0; u < WF_GROUP / 2; u++) {
       const float4 A = tab[j + 2 * u], B = tab[j + 2 * u + 1];
@@ -251,14 +256,14 @@ RTB_DEVINL void sweep_primary(const float4* __restrict__ tab, const float4* __re
 // ray:  a = u.C - ku, b = v.C - kv, e = a^2 + b^2 - r2'  ->  8 FFMA2 per sphere pair per ray.
 template <int R>
 RTB_DEVINL void sweep_general(const float4* __restrict__ tab, const float4* __restrict__ geom,
-                              const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, int n_pad,
-                              const float (&u)[R][3], const float (&v)[R][3], const float (&nku)[R],
+                              const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, int j_begin,
+                              int j_end, const float (&u)[R][3], const float (&v)[R][3], const float (&nku)[R],
                               const float (&nkv)[R], const uint32_t (&node)[R], const int (&self)[R],
                               const bool (&active)[R], unsigned long long (&best)[R], float eps) {
   uint32_t mask[R];
 #pragma unroll
   for (int q = 0; q < R; q++) { best[q] = KEY_NONE; mask[q] = 0; }
-  for (int j = 0; j < n_pad; j += WF_GROUP) {
+  for (int j = j_begin; j < j_end; j += WF_GROUP) {
 #pragma unroll
     for (int p = 0; p < WF_GROUP / 2; p++) {
       const float4 A = tab[j + 2 * p], B = tab[j + 2 * p + 1];
@@ -476,17 +481,83 @@ RTB_DEVINL uint32_t tail_rays(uint32_t count, int r, int r_small) {
   return (t / q) * q;
 }
 
-template <bool PRIMARY, int R>
+// Per-ray sweep operands.  PRIMARY: a = -dir (ray generated in fp64, rounded once).  General: a = u, b = v
+// (unit vectors completing dir to an orthonormal basis), nku = -(u.org), nkv = -(v.org), self = the sphere
+// the ray starts on (hit_i of its parent node).
+template <bool PRIMARY>
+RTB_DEVINL void ray_setup(const WfParams& P, uint32_t node, float (&a)[3], float (&b)[3], float& nku, float& nkv,
+                          int& self) {
+  if (PRIMARY) {
+    const int W = P.fr64.width;
+    const uint32_t pix = node / (uint32_t)P.spp;
+    const uint32_t sub = node - pix * (uint32_t)P.spp;
+    const int lrow = P.band_l0 + (int)(pix / (uint32_t)W);
+    const int g = P.fr64.spp_grid;
+    double ray[3];
+    primary_ray<double>(P.fr64, (int)(pix % (uint32_t)W), P.rm.local_to_y(lrow), (int)(sub % g), (int)(sub / g), ray);
+    a[0] = -(float)ray[0]; a[1] = -(float)ray[1]; a[2] = -(float)ray[2];
+  } else {
+    const float4 ro = P.b.ray_o[node], rd = P.b.ray_d[node];
+    self = __float_as_int(P.b.pos[P.b.link[node].x].w);
+    const float dx = ro.w, dy = rd.x, dz = rd.y;
+    // branchless orthonormal basis (Duff et al. 2017): u, v unit, u.v = u.d = v.d = 0 to ~1 ulp
+    const float sg = copysignf(1.f, dz);
+    const float ka = -1.f / (sg + dz);
+    const float kb = dx * dy * ka;
+    a[0] = 1.f + sg * dx * dx * ka; a[1] = sg * kb; a[2] = -sg * dx;
+    b[0] = kb; b[1] = sg + dy * dy * ka; b[2] = -dy;
+    nku = -(a[0] * ro.x + a[1] * ro.y + a[2] * ro.z);
+    nkv = -(b[0] * ro.x + b[1] * ro.y + b[2] * ro.z);
+  }
+}
+
+// The ray as process_hit wants it (origin, direction, tree position).  nd = -dir of a primary ray.
+template <bool PRIMARY>
+RTB_DEVINL WfRay ray_record(const WfParams& P, uint32_t node, bool active, float ndx, float ndy, float ndz) {
+  WfRay r;
+  r.node = node;
+  r.active = active;
+  r.path = 1; r.pixsub = node; r.segs_left = P.fr64.segs;
+  r.o[0] = P.origin[0]; r.o[1] = P.origin[1]; r.o[2] = P.origin[2];
+  r.d[0] = -ndx; r.d[1] = -ndy; r.d[2] = -ndz;
+  if (!PRIMARY) {
+    r.d[0] = r.d[1] = r.d[2] = 0.f;
+    if (active) {
+      const float4 ro = P.b.ray_o[node], rd = P.b.ray_d[node];
+      const int2 lk = P.b.link[node];
+      r.o[0] = ro.x; r.o[1] = ro.y; r.o[2] = ro.z;
+      r.d[0] = ro.w; r.d[1] = rd.x; r.d[2] = rd.y;
+      r.path = (uint32_t)lk.y & 0xffffffu;
+      r.segs_left = (int)((uint32_t)lk.y >> 24);
+      r.pixsub = __float_as_uint(rd.w);                  // pixel*spp+sub of the level-1 ancestor
+    }
+  }
+  return r;
+}
+
+// CTA_FETCH: the CTA takes eight consecutive chunks per fetch (one per warp) so that its warps reach
+// the end of the range together — required when a team phase (CTA-wide barriers) follows.
+template <bool PRIMARY, int R, bool CTA_FETCH>
 RTB_DEVINL void trace_chunks(const WfParams& P, uint32_t* work, const float4* __restrict__ tab, uint32_t begin,
                              uint32_t end, uint32_t lane, unsigned long long& my_nodes) {
   const int n_pad = P.n_pad;
   const float eps = P.sc.eps;
-  const int W = P.fr64.width;
   constexpr uint32_t CHUNK = 32u * R;
+  __shared__ uint32_t s_first;
 
   for (;;) {
-    const uint64_t base = (uint64_t)begin + (uint64_t)next_chunk(work, lane) * CHUNK;
-    if (base >= end) break;
+    uint32_t c;
+    if (CTA_FETCH) {
+      __syncthreads();
+      if (threadIdx.x == 0) s_first = atomicAdd(work, (uint32_t)WF_WARPS);
+      __syncthreads();
+      if ((uint64_t)begin + (uint64_t)s_first * CHUNK >= end) break;
+      c = s_first + (threadIdx.x >> 5);
+    } else {
+      c = next_chunk(work, lane);
+    }
+    const uint64_t base = (uint64_t)begin + (uint64_t)c * CHUNK;
+    if (base >= end) { if (CTA_FETCH) continue; else break; }
     float a[R][3], b[R][3];          // PRIMARY: a = -dir;  general: a = u, b = v (basis completing dir)
     float nku[R], nkv[R];            // general: -(u.org), -(v.org)
     uint32_t nodes[R];
@@ -506,53 +577,78 @@ RTB_DEVINL void trace_chunks(const WfParams& P, uint32_t* work, const float4* __
       self[q] = -1;
       if (active[q]) {
         my_nodes++;
-        if (PRIMARY) {
-          const uint32_t pix = node / (uint32_t)P.spp;
-          const uint32_t sub = node - pix * (uint32_t)P.spp;
-          const int lrow = P.band_l0 + (int)(pix / (uint32_t)W);
-          const int g = P.fr64.spp_grid;
-          double ray[3];
-          primary_ray<double>(P.fr64, (int)(pix % (uint32_t)W), P.rm.local_to_y(lrow), (int)(sub % g), (int)(sub / g), ray);
-          a[q][0] = -(float)ray[0]; a[q][1] = -(float)ray[1]; a[q][2] = -(float)ray[2];
-        } else {
-          const float4 ro = P.b.ray_o[node], rd = P.b.ray_d[node];
-          self[q] = __float_as_int(P.b.pos[P.b.link[node].x].w);
-          const float dx = ro.w, dy = rd.x, dz = rd.y;
-          // branchless orthonormal basis (Duff et al. 2017): u, v unit, u.v = u.d = v.d = 0 to ~1 ulp
-          const float sg = copysignf(1.f, dz);
-          const float ka = -1.f / (sg + dz);
-          const float kb = dx * dy * ka;
-          a[q][0] = 1.f + sg * dx * dx * ka; a[q][1] = sg * kb; a[q][2] = -sg * dx;
-          b[q][0] = kb; b[q][1] = sg + dy * dy * ka; b[q][2] = -dy;
-          nku[q] = -(a[q][0] * ro.x + a[q][1] * ro.y + a[q][2] * ro.z);
-          nkv[q] = -(b[q][0] * ro.x + b[q][1] * ro.y + b[q][2] * ro.z);
-        }
+        ray_setup<PRIMARY>(P, node, a[q], b[q], nku[q], nkv[q], self[q]);
       }
     }
-    if (PRIMARY) sweep_primary<R>(tab, P.primary_x, n_pad, a, active, best, eps);
-    else sweep_general<R>(tab, P.geom, P.b.ray_o, P.b.ray_d, n_pad, a, b, nku, nkv, nodes, self, active, best, eps);
+    if (PRIMARY) sweep_primary<R>(tab, P.primary_x, 0, n_pad, a, active, best, eps);
+    else sweep_general<R>(tab, P.geom, P.b.ray_o, P.b.ray_d, 0, n_pad, a, b, nku, nkv, nodes, self, active, best, eps);
     __syncwarp();
 #pragma unroll
+    for (int q = 0; q < R; q++)
+      process_hit(P, ray_record<PRIMARY>(P, nodes[q], active[q], a[q][0], a[q][1], a[q][2]), best[q], lane);
+  }
+}
+
+// TEAM mode: the whole CTA works on ONE chunk of 32 x R_TEAM rays.  Every warp sweeps its own eighth of
+// the sphere table for all of the chunk's rays, the closest-hit keys are min-reduced through shared
+// memory (the key order is total, so the result is the one a single sweep would find), and warps
+// 0..R_TEAM-1 then run process_hit with one ray per lane.  A chunk lasts an eighth as long as a
+// whole-table chunk and occupies all four schedulers of the SM evenly, which is what small levels
+// (deep recursion, one stripe set of a multi-GPU frame) and the tail of large ones need: the launch
+// ends within one short chunk of the moment the work runs out.
+template <bool PRIMARY>
+RTB_DEVINL void trace_team(const WfParams& P, uint32_t* work, const float4* __restrict__ tab, uint32_t begin,
+                           uint32_t end, unsigned long long& my_nodes) {
+  constexpr int R = R_TEAM;
+  constexpr uint32_t CHUNK = 32u * R;
+  __shared__ unsigned long long s_best[WF_WARPS][CHUNK];
+  __shared__ uint32_t s_chunk[2];
+  const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+  const float eps = P.sc.eps;
+  // slice of the table in sweep groups
+  const int groups = P.n_pad / WF_GROUP;
+  const int j_begin = (int)((w * (uint32_t)groups) / WF_WARPS) * WF_GROUP;
+  const int j_end = (int)(((w + 1u) * (uint32_t)groups) / WF_WARPS) * WF_GROUP;
+
+  if (threadIdx.x == 0) s_chunk[0] = atomicAdd(work, 1u);
+  for (uint32_t it = 0;; it++) {
+    __syncthreads();                                       // chunk id visible, s_best free again
+    const uint64_t base = (uint64_t)begin + (uint64_t)s_chunk[it & 1u] * CHUNK;
+    if (base >= end) break;
+    float a[R][3], b[R][3], nku[R], nkv[R];
+    uint32_t nodes[R];
+    int self[R];
+    bool active[R];
+    unsigned long long best[R];
+#pragma unroll
     for (int q = 0; q < R; q++) {
-      WfRay r;
-      r.node = nodes[q];
-      r.active = active[q];
-      r.path = 1; r.pixsub = r.node; r.segs_left = P.fr64.segs;
-      r.o[0] = P.origin[0]; r.o[1] = P.origin[1]; r.o[2] = P.origin[2];
-      r.d[0] = -a[q][0]; r.d[1] = -a[q][1]; r.d[2] = -a[q][2];
-      if (!PRIMARY) {
-        r.d[0] = r.d[1] = r.d[2] = 0.f;
-        if (r.active) {
-          const float4 ro = P.b.ray_o[r.node], rd = P.b.ray_d[r.node];
-          const int2 lk = P.b.link[r.node];
-          r.o[0] = ro.x; r.o[1] = ro.y; r.o[2] = ro.z;
-          r.d[0] = ro.w; r.d[1] = rd.x; r.d[2] = rd.y;
-          r.path = (uint32_t)lk.y & 0xffffffu;
-          r.segs_left = (int)((uint32_t)lk.y >> 24);
-          r.pixsub = __float_as_uint(rd.w);                  // pixel*spp+sub of the level-1 ancestor
-        }
-      }
-      process_hit(P, r, best[q], lane);
+      const uint32_t node = (uint32_t)base + (uint32_t)q * 32u + lane;
+      nodes[q] = node;
+      active[q] = node < end;
+      a[q][0] = a[q][1] = a[q][2] = 0.f;
+      b[q][0] = b[q][1] = b[q][2] = 0.f;
+      nku[q] = 3.0e18f; nkv[q] = 0.f;
+      self[q] = -1;
+      if (active[q]) ray_setup<PRIMARY>(P, node, a[q], b[q], nku[q], nkv[q], self[q]);
+    }
+    if (PRIMARY) sweep_primary<R>(tab, P.primary_x, j_begin, j_end, a, active, best, eps);
+    else sweep_general<R>(tab, P.geom, P.b.ray_o, P.b.ray_d, j_begin, j_end, a, b, nku, nkv, nodes, self, active, best, eps);
+#pragma unroll
+    for (int q = 0; q < R; q++) s_best[w][q * 32 + lane] = best[q];
+    __syncthreads();
+    if (threadIdx.x == 0) s_chunk[(it + 1u) & 1u] = atomicAdd(work, 1u);   // slot last read before the barrier above
+    if (w < (uint32_t)R) {
+      const uint32_t slot = w * 32u + lane;
+      unsigned long long key = s_best[0][slot];
+#pragma unroll
+      for (int v = 1; v < WF_WARPS; v++) { const unsigned long long k2 = s_best[v][slot]; if (k2 < key) key = k2; }
+      float nd[3] = {0.f, 0.f, 0.f};
+      bool act = false;
+#pragma unroll
+      for (int q = 0; q < R; q++)
+        if ((uint32_t)q == w) { nd[0] = a[q][0]; nd[1] = a[q][1]; nd[2] = a[q][2]; act = active[q]; }
+      if (act) my_nodes++;
+      process_hit(P, ray_record<PRIMARY>(P, (uint32_t)base + slot, act, nd[0], nd[1], nd[2]), key, lane);
     }
   }
 }
@@ -572,13 +668,27 @@ wf_trace_kernel(const __grid_constant__ WfParams P, int level) {
   level_range(P, level, begin, end);
   const uint32_t lane = threadIdx.x & 31u;
   unsigned long long my_nodes = 0;
-  const int r = pick_rays_per_lane(end - begin, RB, PRIMARY ? 9u : 20u);
-  const uint32_t split = end - tail_rays(end - begin, r, RB / 4);
   uint32_t* wa = &P.b.ctr->work_trace[level];
-  if (r == RB) trace_chunks<PRIMARY, RB>(P, wa, tab, begin, split, lane, my_nodes);
-  else if (r == RB / 2) trace_chunks<PRIMARY, RB / 2>(P, wa, tab, begin, split, lane, my_nodes);
-  else trace_chunks<PRIMARY, RB / 4>(P, wa, tab, begin, split, lane, my_nodes);
-  if (split < end) trace_chunks<PRIMARY, RB / 4>(P, &P.b.ctr->work_trace_tail[level], tab, split, end, lane, my_nodes);
+  uint32_t* wt = &P.b.ctr->work_trace_tail[level];
+  if (P.team_mode == 0) {
+    const int r = P.fixed_r ? (RB >> (P.fixed_r - 1)) : pick_rays_per_lane(end - begin, RB, PRIMARY ? 9u : 20u);
+    const uint32_t split = P.fixed_r ? end : end - tail_rays(end - begin, r, RB / 4);
+    if (r == RB) trace_chunks<PRIMARY, RB, false>(P, wa, tab, begin, split, lane, my_nodes);
+    else if (r == RB / 2) trace_chunks<PRIMARY, RB / 2, false>(P, wa, tab, begin, split, lane, my_nodes);
+    else trace_chunks<PRIMARY, RB / 4, false>(P, wa, tab, begin, split, lane, my_nodes);
+    if (split < end) trace_chunks<PRIMARY, RB / 4, false>(P, wt, tab, split, end, lane, my_nodes);
+  } else {
+    // whole-table chunks for the bulk of a large level, team chunks for its last half round (CTAs leave
+    // the bulk phase up to one round apart) and for small levels altogether
+    const uint32_t count = end - begin;
+    const uint32_t cta_round = (uint32_t)WF_WARPS * 32u * (uint32_t)RB;        // rays per CTA fetch
+    const uint64_t round = (uint64_t)gridDim.x * cta_round;                    // rays per round of the grid
+    uint32_t n_big = 0;
+    if (P.team_mode == 1 && (uint64_t)count >= (uint64_t)P.team_rounds * round)
+      n_big = (uint32_t)(((uint64_t)count - round / 2u) / cta_round) * cta_round;
+    if (n_big) trace_chunks<PRIMARY, RB, true>(P, wa, tab, begin, begin + n_big, lane, my_nodes);
+    trace_team<PRIMARY>(P, wt, tab, begin + n_big, end, my_nodes);
+  }
   // stats
   for (int o2 = 16; o2 > 0; o2 >>= 1) my_nodes += __shfl_down_sync(0xffffffffu, my_nodes, o2);
   if (lane == 0 && my_nodes) {
@@ -714,8 +824,8 @@ wf_shadow_kernel(const __grid_constant__ WfParams P, int k, int phase) {
   const uint32_t lane = threadIdx.x & 31u;
   unsigned long long my_rays = 0, my_tests = 0;
   uint32_t* work_tail = (phase == 1) ? &P.b.ctr->work_shadow_early_tail : &P.b.ctr->work_shadow_tail[k];
-  const int r = pick_rays_per_lane(count - first, R_SHARED, 9u);
-  const uint32_t split = count - tail_rays(count - first, r, R_SHARED / 4);
+  const int r = P.fixed_r ? (R_SHARED >> (P.fixed_r - 1)) : pick_rays_per_lane(count - first, R_SHARED, 9u);
+  const uint32_t split = P.fixed_r ? count : count - tail_rays(count - first, r, R_SHARED / 4);
   if (r == R_SHARED) shadow_chunks<R_SHARED>(P, k, tab, first, split, work, lane, my_rays, my_tests);
   else if (r == R_SHARED / 2) shadow_chunks<R_SHARED / 2>(P, k, tab, first, split, work, lane, my_rays, my_tests);
   else shadow_chunks<R_SHARED / 4>(P, k, tab, first, split, work, lane, my_rays, my_tests);
@@ -807,13 +917,31 @@ size_t per_node_bytes(int n_lights) {
   return 16 * 7 + 8 + (n_lights > 2 ? 16 : 0) + 4 * (size_t)n_lights;
 }
 
-int ensure_workspace(int n_lights, uint32_t cap_nodes) {
-  WfBuffers& b = g_rtb.wf;
+void slot_free(WfSlot& sl) {
+  WfBuffers& b = sl.wf;
+  cudaFree(b.ray_o); cudaFree(b.ray_d); cudaFree(b.link); cudaFree(b.pos); cudaFree(b.base);
+  cudaFree(b.lq); cudaFree(b.lq2); cudaFree(b.acc); cudaFree(b.child_a); cudaFree(b.child_b);
+  for (int k = 0; k < RTB_MAX_LIGHTS; k++) cudaFree(b.sq[k]);
+  cudaFree(b.ctr);
+  b = WfBuffers{};
+  sl.wf_lights = 0;
+  sl.wf_bytes = 0;
+}
+
+int ensure_workspace(WfSlot& sl, int n_lights, uint32_t cap_nodes) {
+  WfBuffers& b = sl.wf;
+  if (!sl.stream2) {
+    RTB_CUDA(cudaStreamCreateWithFlags(&sl.stream2, cudaStreamNonBlocking));
+    RTB_CUDA(cudaEventCreateWithFlags(&sl.ev_primary, cudaEventDisableTiming));
+    RTB_CUDA(cudaEventCreateWithFlags(&sl.ev_early, cudaEventDisableTiming));
+    RTB_CUDA(cudaEventCreateWithFlags(&sl.ev_async, cudaEventDisableTiming));
+    RTB_CUDA(cudaMallocHost(&sl.h_sticky, sizeof(WfSticky)));
+  }
   const bool need_lq2 = n_lights > 2;
-  if (b.cap_nodes >= cap_nodes && b.ctr && g_rtb.wf_lights >= n_lights && (!need_lq2 || b.lq2)) return RTB_OK;
+  if (b.cap_nodes >= cap_nodes && b.ctr && sl.wf_lights >= n_lights && (!need_lq2 || b.lq2)) return RTB_OK;
   const uint32_t cap = std::max(cap_nodes, b.cap_nodes);
-  const int lights = std::max(n_lights, g_rtb.wf_lights);
-  wf_free();
+  const int lights = std::max(n_lights, sl.wf_lights);
+  slot_free(sl);
   const size_t n = cap;
   RTB_CUDA(cudaMalloc(&b.ray_o, n * 16));
   RTB_CUDA(cudaMalloc(&b.ray_d, n * 16));
@@ -828,45 +956,60 @@ int ensure_workspace(int n_lights, uint32_t cap_nodes) {
   for (int k = 0; k < lights; k++) RTB_CUDA(cudaMalloc(&b.sq[k], n * 4));
   RTB_CUDA(cudaMalloc(&b.ctr, sizeof(WfCounters) + sizeof(WfSticky)));
   b.cap_nodes = cap;
-  g_rtb.wf_lights = lights;
-  g_rtb.wf_bytes = n * per_node_bytes(lights);
+  sl.wf_lights = lights;
+  sl.wf_bytes = n * per_node_bytes(lights);
   return RTB_OK;
 }
 
 }  // namespace
 
 void wf_free() {
-  WfBuffers& b = g_rtb.wf;
-  cudaFree(b.ray_o); cudaFree(b.ray_d); cudaFree(b.link); cudaFree(b.pos); cudaFree(b.base);
-  cudaFree(b.lq); cudaFree(b.lq2); cudaFree(b.acc); cudaFree(b.child_a); cudaFree(b.child_b);
-  for (int k = 0; k < RTB_MAX_LIGHTS; k++) cudaFree(b.sq[k]);
-  cudaFree(b.ctr);
-  b = WfBuffers{};
-  g_rtb.wf_lights = 0;
-  g_rtb.wf_bytes = 0;
+  for (WfSlot& sl : g_rtb.slot) {
+    slot_free(sl);
+    if (sl.stream2) cudaStreamDestroy(sl.stream2);
+    if (sl.ev_primary) cudaEventDestroy(sl.ev_primary);
+    if (sl.ev_early) cudaEventDestroy(sl.ev_early);
+    if (sl.ev_async) cudaEventDestroy(sl.ev_async);
+    if (sl.h_sticky) cudaFreeHost(sl.h_sticky);
+    if (sl.h_tab) cudaFreeHost(sl.h_tab);
+    sl = WfSlot{};
+  }
 }
 
-int rtb_finish_pending() {
-  RtbScene_* s = g_rtb.pending_scene;
+static int finish_slot(WfSlot& sl) {
+  RtbScene_* s = sl.pending_scene;
   if (!s) return RTB_OK;
-  g_rtb.pending_scene = nullptr;
-  RTB_CUDA(cudaEventSynchronize(g_rtb.ev_async));
-  const WfSticky& h = *static_cast<const WfSticky*>(g_rtb.h_sticky);
+  sl.pending_scene = nullptr;
+  RTB_CUDA(cudaEventSynchronize(sl.ev_async));
+  const WfSticky& h = *static_cast<const WfSticky*>(sl.h_sticky);
   if (h.overflow) {
-    if (s->pending_rows <= 1) {
+    s->deferred_status = RTB_ERR_OVERFLOW;
+    if (sl.pending_rows <= 1) {
       rtb_set_error("ray queues overflow even with one-row bands");
-      s->deferred_status = RTB_ERR_OVERFLOW;
       return RTB_OK;
     }
-    s->wf_rows_hint = std::max(1, s->pending_rows / 2);   // the same call will now use smaller bands
-    s->deferred_status = RTB_ERR_OVERFLOW;
+    // the same call will now use smaller bands (two frames in flight may both report: keep the smaller)
+    const int hint = std::max(1, sl.pending_rows / 2);
+    s->wf_rows_hint = s->wf_rows_hint > 0 ? std::min(s->wf_rows_hint, hint) : hint;
+  }
+  return RTB_OK;
+}
+
+int rtb_finish_pending(int slot) {
+  if (slot >= 0) return finish_slot(g_rtb.slot[slot % RTB_MAX_IN_FLIGHT]);
+  // oldest first: next_slot is the one that would be reused next
+  for (int i = 0; i < RTB_MAX_IN_FLIGHT; i++) {
+    const int rc = finish_slot(g_rtb.slot[(g_rtb.next_slot + i) % RTB_MAX_IN_FLIGHT]);
+    if (rc != RTB_OK) return rc;
   }
   return RTB_OK;
 }
 
 int wf_render(RtbScene_* s, const RtbCamera* cam, const DevFrameT<float>& fr32, const RowMap& rm,
-              uint8_t* d_out, cudaStream_t st, RtbStats* stats, bool async) {
+              uint8_t* d_out, cudaStream_t st, RtbStats* stats, bool async, int slot) {
   if (stats) async = false;
+  const int ps = slot % RTB_MAX_IN_FLIGHT;                 // also the primary-table set of this slot
+  WfSlot& sl = g_rtb.slot[ps];
   const int W = cam->width;
   const int n_rows = rm.n_local();
   if (n_rows <= 0) return RTB_OK;
@@ -884,17 +1027,24 @@ int wf_render(RtbScene_* s, const RtbCamera* cam, const DevFrameT<float>& fr32, 
   }
 
   // primary tables: per-sphere constants of rays leaving the camera origin, in fp64, rounded once
-  if (!s->primary_valid || s->primary_origin[0] != cam->origin[0] || s->primary_origin[1] != cam->origin[1] ||
-      s->primary_origin[2] != cam->origin[2]) {
-    float4* h_tab = reinterpret_cast<float4*>(g_rtb.h_stage);       // sized >= 2 tables by rtb_scene_create
+  // (one table set and one pinned staging buffer per slot: the slot's previous frame has been collected
+  // before it is reused, so neither is still being read and no host wait is needed here)
+  if (!s->primary_valid[ps] || s->primary_origin[ps][0] != cam->origin[0] ||
+      s->primary_origin[ps][1] != cam->origin[1] || s->primary_origin[ps][2] != cam->origin[2]) {
+    if (sl.h_tab_bytes < 2 * smem) {
+      if (sl.h_tab) { RTB_CUDA(cudaDeviceSynchronize()); cudaFreeHost(sl.h_tab); }
+      sl.h_tab = nullptr; sl.h_tab_bytes = 0;
+      RTB_CUDA(cudaMallocHost(&sl.h_tab, 2 * smem));
+      sl.h_tab_bytes = 2 * smem;
+    }
+    float4* h_tab = reinterpret_cast<float4*>(sl.h_tab);
     float4* h_x = h_tab + n_pad;
     wf_make_table(s->spheres.data(), n, n_pad, cam->origin, h_tab, h_x);
-    RTB_CUDA(cudaMemcpyAsync(s->d_primary_tab, h_tab, smem, cudaMemcpyHostToDevice, st));
-    RTB_CUDA(cudaMemcpyAsync(s->d_primary_x, h_x, smem, cudaMemcpyHostToDevice, st));
-    // the pinned staging buffer is rewritten by the next camera: wait for the copy
-    RTB_CUDA(cudaStreamSynchronize(st));
-    for (int c = 0; c < 3; c++) s->primary_origin[c] = cam->origin[c];
-    s->primary_valid = true;
+    RTB_CUDA(cudaMemcpyAsync(s->d_primary_tab[ps], h_tab, smem, cudaMemcpyHostToDevice, st));
+    RTB_CUDA(cudaMemcpyAsync(s->d_primary_x[ps], h_x, smem, cudaMemcpyHostToDevice, st));
+    if (!async) RTB_CUDA(cudaStreamSynchronize(st));      // synchronous calls may come back on another stream
+    for (int c = 0; c < 3; c++) s->primary_origin[ps][c] = cam->origin[c];
+    s->primary_valid[ps] = true;
   }
 
   const int g = fr32.spp_grid, spp = g * g;
@@ -905,7 +1055,7 @@ int wf_render(RtbScene_* s, const RtbCamera* cam, const DevFrameT<float>& fr32, 
   if (const char* e = getenv("RTB_WF_CAP_NODES")) { const long long v = atoll(e); if (v > 0) cap = (uint64_t)v; }
   if (cap < 4 * sub_per_row) cap = 4 * sub_per_row;      // at least one row per band with headroom
   if (cap > 0xfffffff0ull) { rtb_set_error("frame too wide for the wavefront queues"); return RTB_ERR_UNSUPPORTED; }
-  int rc = ensure_workspace(s->n_lights, (uint32_t)cap);
+  int rc = ensure_workspace(sl, s->n_lights, (uint32_t)cap);
   if (rc != RTB_OK) return rc;
   // the shared workspace may be larger than this call asked for; band sizes and the overflow
   // check follow the REQUESTED capacity so that results do not depend on earlier calls
@@ -923,18 +1073,35 @@ int wf_render(RtbScene_* s, const RtbCamera* cam, const DevFrameT<float>& fr32, 
   }
   f.projW = cam->projW; f.projH = cam->projH; f.projD = cam->projD;
   P.rm = rm;
-  P.b = g_rtb.wf;
+  P.b = sl.wf;
   P.b.cap_nodes = (uint32_t)cap;
   if (s->n_lights <= 2) P.b.lq2 = nullptr;                // kernels key the lights-2/3 store on this
-  P.sticky = reinterpret_cast<WfSticky*>(reinterpret_cast<char*>(g_rtb.wf.ctr) + sizeof(WfCounters));
+  P.sticky = reinterpret_cast<WfSticky*>(reinterpret_cast<char*>(sl.wf.ctr) + sizeof(WfCounters));
   P.geom = reinterpret_cast<const float4*>(s->d_geom32);
   P.geom_tab = s->d_geom_tab;
-  P.primary_tab = s->d_primary_tab;
-  P.primary_x = s->d_primary_x;
+  P.primary_tab = s->d_primary_tab[ps];
+  P.primary_x = s->d_primary_x[ps];
   for (int k = 0; k < s->n_lights; k++) { P.light_tab[k] = s->d_light_tab[k]; P.light_x[k] = s->d_light_x[k]; }
   P.n_pad = n_pad;
   P.spp = spp;
   P.aligned4 = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_out) & 15u) == 0);
+  {
+    // chunk scheduling of the trace kernels; RTB_WF_TEAM / RTB_WF_TEAM_ROUNDS override (experiments)
+    static int team_mode = -1, team_rounds = 2;
+    if (team_mode < 0) {
+      const char* e = getenv("RTB_WF_TEAM");
+      team_mode = e ? std::max(0, std::min(2, atoi(e))) : 0;
+      if (const char* r = getenv("RTB_WF_TEAM_ROUNDS")) team_rounds = std::max(1, atoi(r));
+    }
+    static int fixed_r = -1;
+    if (fixed_r < 0) { const char* e = getenv("RTB_WF_FIXED_R"); fixed_r = e ? std::max(0, std::min(3, atoi(e))) : 0; }
+    // Three or more frames in flight: other frames' kernels fill this frame's tails, so the chunk size
+    // that is cheapest per ray wins over the one that ends a lone launch soonest (measured, 1/8 of a 4K
+    // frame per GPU: 1.37 -> 1.28 ms per frame).
+    P.fixed_r = fixed_r ? fixed_r : (async && g_rtb.frames_in_flight >= 3 ? 1 : 0);
+    P.team_mode = team_mode;
+    P.team_rounds = (uint32_t)team_rounds;
+  }
 
   // persistent grids: as many CTAs as fit, per kernel
   auto grid_for = [&](const void* fn, size_t sm) -> int {
@@ -955,8 +1122,7 @@ int wf_render(RtbScene_* s, const RtbCamera* cam, const DevFrameT<float>& fr32, 
 
   int rows_per_band = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)n_rows, (cap / 3) / sub_per_row));
   if (s->wf_rows_hint > 0 && s->wf_rows_hint < rows_per_band) rows_per_band = s->wf_rows_hint;   // learnt earlier
-  if (!g_rtb.h_sticky) RTB_CUDA(cudaMallocHost(&g_rtb.h_sticky, sizeof(WfSticky)));
-  WfSticky& h_sticky = *static_cast<WfSticky*>(g_rtb.h_sticky);
+  WfSticky& h_sticky = *static_cast<WfSticky*>(sl.h_sticky);
   uint32_t launches = 0, bands = 0;
   // per-class timing (stats only): an event after every class of every band, classes tagged
   enum { T_START = 0, T_PRIMARY, T_SECONDARY, T_SHADOW, T_COMPOSE };
@@ -981,7 +1147,7 @@ int wf_render(RtbScene_* s, const RtbCamera* cam, const DevFrameT<float>& fr32, 
       P.band_rows = std::min(rows_per_band, n_rows - l0);
       P.n_sub = (uint32_t)((uint64_t)P.band_rows * sub_per_row);
       bands++;
-      RTB_CUDA(cudaMemsetAsync(g_rtb.wf.ctr, 0, sizeof(WfCounters), st));
+      RTB_CUDA(cudaMemsetAsync(sl.wf.ctr, 0, sizeof(WfCounters), st));
       if ((rc = mark(T_START)) != RTB_OK) return rc;
       wf_trace_kernel<true><<<grid_p, WF_THREADS, smem, st>>>(P, 1);
       launches++;
@@ -990,18 +1156,18 @@ int wf_render(RtbScene_* s, const RtbCamera* cam, const DevFrameT<float>& fr32, 
       // concurrently with the secondary trace levels (independent work; fills their tails).
       const bool overlap = !stats && s->n_lights > 0 && fr32.segs > 1;
       if (overlap) {
-        RTB_CUDA(cudaEventRecord(g_rtb.ev_primary, st));
-        RTB_CUDA(cudaStreamWaitEvent(g_rtb.stream2, g_rtb.ev_primary, 0));
-        wf_shadow_kernel<<<grid_l, WF_THREADS, smem, g_rtb.stream2>>>(P, 0, 1);
+        RTB_CUDA(cudaEventRecord(sl.ev_primary, st));
+        RTB_CUDA(cudaStreamWaitEvent(sl.stream2, sl.ev_primary, 0));
+        wf_shadow_kernel<<<grid_l, WF_THREADS, smem, sl.stream2>>>(P, 0, 1);
         launches++;
-        RTB_CUDA(cudaEventRecord(g_rtb.ev_early, g_rtb.stream2));
+        RTB_CUDA(cudaEventRecord(sl.ev_early, sl.stream2));
       }
       for (int L = 2; L <= fr32.segs; L++) {
         wf_trace_kernel<false><<<grid_s, WF_THREADS, smem, st>>>(P, L);
         launches++;
       }
       if ((rc = mark(T_SECONDARY)) != RTB_OK) return rc;
-      if (overlap) RTB_CUDA(cudaStreamWaitEvent(st, g_rtb.ev_early, 0));
+      if (overlap) RTB_CUDA(cudaStreamWaitEvent(st, sl.ev_early, 0));
       for (int k = 0; k < s->n_lights; k++) {
         wf_shadow_kernel<<<grid_l, WF_THREADS, smem, st>>>(P, k, (k == 0 && overlap) ? 2 : 0);
         launches++;
@@ -1018,9 +1184,10 @@ int wf_render(RtbScene_* s, const RtbCamera* cam, const DevFrameT<float>& fr32, 
     }
     RTB_CUDA(cudaMemcpyAsync(&h_sticky, P.sticky, sizeof h_sticky, cudaMemcpyDeviceToHost, st));
     if (async) {                                          // verdict collected by rtb_finish_pending()
-      RTB_CUDA(cudaEventRecord(g_rtb.ev_async, st));
-      g_rtb.pending_scene = s;
-      s->pending_rows = rows_per_band;
+      RTB_CUDA(cudaEventRecord(sl.ev_async, st));
+      sl.pending_scene = s;
+      sl.pending_rows = rows_per_band;
+      g_rtb.last_slot = ps;
       return RTB_OK;
     }
     RTB_CUDA(cudaStreamSynchronize(st));

@@ -21,7 +21,10 @@ import numpy as np
 from . import _abi as A
 from .scene import make_opts
 
-DEFAULT_STRIPE_ROWS = 4     # 2160 rows / 4 = 540 stripes: per-rank row counts differ by < 1.5 % at 8 ranks
+DEFAULT_STRIPE_ROWS = 4
+MAX_IN_FLIGHT = 4            # = RTB_MAX_IN_FLIGHT of the library
+DEFAULT_IN_FLIGHT = 3        # frames redraw_sequence keeps in flight (measured: 1.67 / 1.41 / 1.28 / 1.25 ms per
+                             # 1/8-frame for 1 / 2 / 3 / 4 on one B200)     # 2160 rows / 4 = 540 stripes: per-rank row counts differ by < 1.5 % at 8 ranks
 
 
 # ---- partition arithmetic (mirrors RowMap in csrc/rtb_device.cuh; tested against it) ----------------
@@ -89,18 +92,26 @@ class StripedRenderer:
         self.stride = self.padded + 1
         dev = torch.device("cuda", torch.cuda.current_device())
         self.dev = dev
-        self.frame = torch.empty((height, width, 4), dtype=torch.uint8, device=dev)
+        # MAX_IN_FLIGHT sets of everything: redraw_sequence keeps several frames in flight
+        K = MAX_IN_FLIGHT
+        self.frames = [torch.empty((height, width, 4), dtype=torch.uint8, device=dev) for _ in range(K)]
+        self.frame = self.frames[0]
+        self.flags_host = [torch.zeros((max(world, 1),), dtype=torch.int32).pin_memory() for _ in range(K)]
+        self.status_dev = torch.zeros((K, 4), dtype=torch.int32, device=dev)      # world == 1: status words
+        self._streams = None
         if world > 1:
-            # two sets: frame i+1 renders while frame i is still being gathered (redraw_sequence)
-            self.local = [torch.zeros((self.stride, width, 4), dtype=torch.uint8, device=dev) for _ in range(2)]
-            self.gathered = [torch.empty((world, self.stride, width, 4), dtype=torch.uint8, device=dev) for _ in range(2)]
-            self.flags_host = torch.zeros((world,), dtype=torch.int32).pin_memory()
+            self.local = [torch.zeros((self.stride, width, 4), dtype=torch.uint8, device=dev) for _ in range(K)]
+            self.gathered = [torch.empty((world, self.stride, width, 4), dtype=torch.uint8, device=dev) for _ in range(K)]
 
-    # -- building blocks ---------------------------------------------------------------------------
+    # -- building blocks (everything is enqueued on the CURRENT torch stream) --------------------------
     def _enqueue_render(self, camera, slot, stats, kw):
         import torch
 
         stream = torch.cuda.current_stream().cuda_stream
+        if self.world <= 1:
+            self.r.redraw_device(camera, make_opts(**kw), self.frames[slot].data_ptr(), stream, stats)
+            A.check(self.lib.rtb_copy_status_device(self.r._h, self.status_dev[slot].data_ptr(), A.stream_arg(stream)))
+            return
         o = make_opts(stripe_rows=self.S, stripe_rank=self.rank, stripe_world=self.world, out_packed=1, **kw)
         loc = self.local[slot]
         self.r.redraw_device(camera, o, loc.data_ptr(), stream, stats)
@@ -116,18 +127,19 @@ class StripedRenderer:
         import torch
 
         stream = torch.cuda.current_stream().cuda_stream
-        A.check(self.lib.rtb_unstripe_device(self.gathered[slot].data_ptr(), self.frame.data_ptr(), self.W, self.H,
-                                             self.S, self.world, self.stride, A.stream_arg(stream)))
+        A.check(self.lib.rtb_unstripe_device(self.gathered[slot].data_ptr(), self.frames[slot].data_ptr(), self.W,
+                                             self.H, self.S, self.world, self.stride, A.stream_arg(stream)))
         flags = self.gathered[slot][:, self.padded, 0, :].contiguous().view(torch.int32).view(-1)
-        self.flags_host.copy_(flags, non_blocking=True)
+        self.flags_host[slot].copy_(flags, non_blocking=True)
 
-    def _verdict(self) -> bool:
-        """Host-side: wait for the current stream, collect this rank's deferred status, read all flags."""
-        import torch
-
-        torch.cuda.current_stream().synchronize()
-        self.r.finish()                                   # clears the library's pending state (already complete)
-        return not bool(self.flags_host.any())
+    def _enqueue_frame(self, camera, slot, kw):
+        """Render (+ gather + de-interleave) of one frame into self.frames[slot]; status words to the host."""
+        self._enqueue_render(camera, slot, None, kw)
+        if self.world > 1:
+            self._enqueue_gather(slot).wait()             # stream-level wait, the host does not block
+            self._enqueue_unstripe(slot)
+        else:
+            self.flags_host[slot].copy_(self.status_dev[slot, :1], non_blocking=True)
 
     # -- one frame (latency mode) ----------------------------------------------------------------------
     def redraw(self, camera, stats=None, **kw):
@@ -137,78 +149,75 @@ class StripedRenderer:
         offending rank's bands, deterministically)."""
         import torch
 
-        stream = torch.cuda.current_stream().cuda_stream
-        if self.world <= 1:
-            while True:
-                self.r.redraw_device(camera, make_opts(**kw), self.frame.data_ptr(), stream, stats)
-                if self.r.finish():
-                    return self.frame
         while True:
-            self._enqueue_render(camera, 0, stats, kw)
-            self._enqueue_gather(0).wait()
-            self._enqueue_unstripe(0)
-            if self._verdict():
+            if stats is not None:
+                self._enqueue_render(camera, 0, stats, kw)
+                if self.world > 1:
+                    self._enqueue_gather(0).wait()
+                    self._enqueue_unstripe(0)
+                else:
+                    self.flags_host[0].copy_(self.status_dev[0, :1], non_blocking=True)
+            else:
+                self._enqueue_frame(camera, 0, kw)
+            torch.cuda.current_stream().synchronize()
+            self.r.finish()                               # clears the library's pending state (already complete)
+            if not bool(self.flags_host[0].any()):
+                self.frame = self.frames[0]
                 return self.frame
 
     # -- a sequence of frames (throughput mode) ----------------------------------------------------------
-    def redraw_sequence(self, cameras, on_frame=None, **kw):
-        """Software-pipelined: frame i+1 is rendered while frame i is in the collective.  `on_frame(i,
-        frame)` is called (device tensor, valid until the next call) once frame i is assembled.  Returns
-        the number of frames that had to be repeated because of queue overflows."""
+    def redraw_sequence(self, cameras, on_frame=None, frames_in_flight: int = DEFAULT_IN_FLIGHT, **kw):
+        """Software-pipelined: up to `frames_in_flight` (1..4) frames are enqueued before the host waits
+        for the oldest one, each on its own stream with its own library workspace.  Later frames render
+        while frame i is in the collective, and the kernels of the frames interleave on the GPU: the
+        short per-level launches of one fill the tails of the others.  `on_frame(i, frame)` is called
+        (device tensor, valid for the next frames_in_flight - 1 calls) once frame i is assembled on this
+        rank.  Returns the number of frames that had to be repeated because of queue overflows (every
+        rank reads the same gathered status words, so every rank repeats the same frames)."""
         import torch
 
-        stream = torch.cuda.current_stream().cuda_stream
+        depth = max(1, min(MAX_IN_FLIGHT, int(frames_in_flight)))
         n = len(cameras)
-        if self.world <= 1:
-            repeats = 0
-            for i, c in enumerate(cameras):
-                while True:
-                    self.r.redraw_device(c, make_opts(**kw), self.frame.data_ptr(), stream, None)
-                    if self.r.finish():
-                        break
-                    repeats += 1
-                if on_frame:
-                    on_frame(i, self.frame)
-            return repeats
+        main = torch.cuda.current_stream()
+        if self._streams is None:
+            self._streams = [torch.cuda.Stream(device=self.dev) for _ in range(MAX_IN_FLIGHT)]
+        done = [torch.cuda.Event() for _ in range(MAX_IN_FLIGHT)]
+        for st in self._streams:
+            st.wait_stream(main)
+        self.r.set_frames_in_flight(depth)
         repeats = 0
         i = 0
-        work = None
-        while i < n or work is not None:
-            # enqueue the next render first so that it overlaps the collective of the previous frame
-            nxt = None
-            if i < n:
-                slot = i & 1
-                try:
-                    self._enqueue_render(cameras[i], slot, None, kw)
-                    nxt = (i, slot)
-                except A.RtbError as e:
-                    # enqueueing collected the verdict of the frame in flight: THIS rank overflowed on it.
-                    # Nothing was enqueued; fall through to that frame's status words so that every rank
-                    # restarts at the same frame.
-                    if e.code != A.RTB_ERR_OVERFLOW or work is None:
-                        raise
-            if work is not None:
-                (j, jslot), w = work
-                w.wait()
-                self._enqueue_unstripe(jslot)
-                ev = torch.cuda.Event()
-                ev.record()
-                ev.synchronize()                          # host waits for frame j only; frame i keeps the GPU busy
-                if bool(self.flags_host.any()):           # same words on every rank: same decision everywhere
+        inflight = []
+        try:
+            while i < n or inflight:
+                while i < n and len(inflight) < depth:
+                    slot = i % depth
+                    with torch.cuda.stream(self._streams[slot]):
+                        self._enqueue_frame(cameras[i], slot, kw)
+                        done[slot].record()
+                    inflight.append(i)
+                    i += 1
+                j = inflight.pop(0)
+                jslot = j % depth
+                done[jslot].synchronize()                 # the host waits for frame j only
+                if bool(self.flags_host[jslot].any()):    # same words on every rank: same decision everywhere
                     repeats += 1
-                    torch.cuda.current_stream().synchronize()
-                    self.r.finish()
-                    i, work = j, None                     # restart the pipeline at frame j
+                    for st in self._streams:
+                        st.synchronize()
+                    self.r.finish()                       # collects every frame in flight; bands were shrunk
+                    i, inflight = j, []                   # restart the pipeline at frame j
                     continue
+                self.frame = self.frames[jslot]
                 if on_frame:
-                    on_frame(j, self.frame)
-            if nxt is not None:
-                work = (nxt, self._enqueue_gather(nxt[1]))
-                i += 1
-            else:
-                work = None
-        torch.cuda.current_stream().synchronize()
-        self.r.finish()
+                    with torch.cuda.stream(self._streams[jslot]):
+                        on_frame(j, self.frame)
+        finally:
+            for st in self._streams:
+                st.synchronize()
+            self.r.finish()
+            self.r.set_frames_in_flight(1)
+            for st in self._streams:
+                main.wait_stream(st)
         return repeats
 
 

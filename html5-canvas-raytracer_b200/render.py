@@ -87,6 +87,11 @@ class Renderer:
         A.check(rc)
         return True
 
+    def set_frames_in_flight(self, n: int) -> None:
+        """1 (default) or 2 asynchronous wavefront frames in flight (rtb_set_frames_in_flight): with 2,
+        consecutive redraw_device() calls on two streams overlap on the GPU."""
+        A.check(self._lib.rtb_set_frames_in_flight(int(n)))
+
     def redraw_batch(self, cameras, out: Optional[np.ndarray] = None, stats: bool = False, opts=None, **kw):
         """Frame batch (orbit animation, BASELINE config 5): F x H x W x 4 uint8."""
         cams = [self._cam(c) for c in cameras]

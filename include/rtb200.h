@@ -206,6 +206,14 @@ int rtb_render_device(rtb_scene_t scene, const RtbCamera* cam, const RtbRenderOp
  * collected is returned by the next render call on the scene instead. */
 int rtb_finish(rtb_scene_t scene);
 
+/* How many asynchronous wavefront frames (rtb_render_device with stats == NULL) the library keeps in
+ * flight: 1 (default) .. 4.  With n > 1, consecutive calls rotate through n private workspaces, and the
+ * call for frame k+n - not the one for frame k+1 - is what collects frame k.  Issued on different
+ * streams, the short per-level kernels of neighbouring frames then run concurrently and fill each
+ * other's tails (sequences; a striped multi-GPU frame is a sequence of small frames).  rtb_finish() waits
+ * for every frame in flight; rtb_copy_status_device() refers to the frame enqueued last. */
+int rtb_set_frames_in_flight(int32_t n);
+
 /* Enqueue, on `cuda_stream`, a 4-byte device-to-device copy of the overflow flag of the frame just
  * enqueued for `scene` (0 = valid, non-zero = ray queues overflowed) to `d_dst_u32`.  Lets a multi-GPU
  * caller ship every rank's verdict inside the all-gather payload, so that all ranks take the same

@@ -293,6 +293,41 @@ def test_striped_renderer_single_rank_sequence(rt, synth):
     rep = sr.redraw_sequence([cam, cam, cam], on_frame=lambda i, fr: seen.append((i, fr.cpu().numpy().copy())), segs=6)
     assert rep == 0 and [i for i, _ in seen] == [0, 1, 2]
     assert all(np.array_equal(a, ref) for _, a in seen)
+    # a moving camera with several frames in flight (one workspace, primary-table set and stream each):
+    # every frame must be the frame a plain redraw of that camera gives, with one frame in flight too
+    cams = rt.scenes.orbit_cameras(192, 108, 7)
+    refs = [synth.redraw(c, segs=6, kernel=rt.RTB_KERNEL_WAVEFRONT) for c in cams]
+    assert any(not np.array_equal(refs[0], x) for x in refs[1:])
+    for depth in (4, 3, 2, 1):
+        seen = []
+        rep = sr.redraw_sequence(cams, on_frame=lambda i, fr: seen.append((i, fr.cpu().numpy().copy())),
+                                 frames_in_flight=depth, segs=6, kernel=rt.RTB_KERNEL_WAVEFRONT)
+        assert rep == 0 and [i for i, _ in seen] == list(range(7))
+        assert all(np.array_equal(a, refs[i]) for i, a in seen), depth
+
+
+def test_two_frames_in_flight_overflow_restarts_the_pipeline(rt):
+    """Forced queue overflow while two frames are in flight: the sequence repeats the frame (smaller
+    bands) and still delivers every frame byte-identical to an unconstrained render."""
+    torch = pytest.importorskip("torch")
+    import os
+    mg = __import__("importlib").import_module("html5-canvas-raytracer_b200.multigpu")
+    objs = rt.scenes.synth_objects(1024, 1024)
+    cams = rt.scenes.orbit_cameras(160, 90, 4)
+    with rt.Renderer(objs) as r0:
+        refs = [r0.redraw(c, segs=6, kernel=rt.RTB_KERNEL_WAVEFRONT) for c in cams]
+    os.environ["RTB_WF_CAP_NODES"] = str(160 * 24)
+    try:
+        with rt.Renderer(objs) as r:
+            sr = mg.StripedRenderer(r, 160, 90, 0, 1)
+            seen = {}
+            rep = sr.redraw_sequence(cams, on_frame=lambda i, fr: seen.__setitem__(i, fr.cpu().numpy().copy()),
+                                     segs=6, kernel=rt.RTB_KERNEL_WAVEFRONT)
+            assert rep >= 1
+            assert sorted(seen) == [0, 1, 2, 3]
+            assert all(np.array_equal(seen[i], refs[i]) for i in range(4))
+    finally:
+        del os.environ["RTB_WF_CAP_NODES"]
 
 
 def test_star_stream_replay_matches_unmodified_main_js(rt, oracle, demo):

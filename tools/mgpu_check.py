@@ -15,7 +15,7 @@ torch.cuda.set_device(local_rank)
 W, H = 640, 362
 objs = rt.scenes.synth_objects(256, 11)
 demo = rt.scenes.demo_objects()
-cams = rt.scenes.orbit_cameras(W, H, nframes=6)[:4]
+cams = rt.scenes.orbit_cameras(W, H, nframes=12)[:9]
 kw = dict(segs=8, kernel=rt.RTB_KERNEL_WAVEFRONT)
 with rt.Renderer(objs, device=local_rank) as r:
     refs = [r.redraw(c, **kw) for c in cams]                       # single-GPU frames (every rank computes them)
@@ -26,7 +26,7 @@ with rt.Renderer(objs, device=local_rank) as r:
         same = bool(np.array_equal(f, ref))
         if not same:
             bad = np.argwhere((f != ref).any(axis=2))
-            print(f"rank {rank}: single frame {ci} differs in {len(bad)} px, rows {sorted(set(bad[:,0].tolist()))[:12]} flags {sr.flags_host.tolist()}", flush=True)
+            print(f"rank {rank}: single frame {ci} differs in {len(bad)} px, rows {sorted(set(bad[:,0].tolist()))[:12]} flags {[f.tolist() for f in sr.flags_host]}", flush=True)
         ok &= same
     got = {}
     rep = sr.redraw_sequence(cams, on_frame=lambda i, fr: got.__setitem__(i, fr.cpu().numpy().copy()), **kw)
