@@ -170,6 +170,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"],
+                    help="multi-GPU framebuffer exchange: peer-memory scatter kernel or NCCL all-gather")
     ap.add_argument("--frames-in-flight", type=int, default=0,
                     help="frames the sequence keeps in flight (0 = the host layer's default)")
     ap.add_argument("--config", default=CONFIG,
@@ -202,7 +204,8 @@ def main():
     objs = build_objects(rt, scene)
     cam = rt.scenes.demo_camera(W, H)
     renderer = rt.Renderer(objs, device=local_rank)
-    sr = mg.StripedRenderer(renderer, W, H, rank, world)
+    sr = mg.StripedRenderer(renderer, W, H, rank, world, exchange=args.exchange)
+    xl = 0 if world <= 1 else (4 if sr.exchange == "p2p" else 1)    # own exchange kernels per frame
     A = rt._abi
     # the product's own choice (RTB_KERNEL_AUTO): wavefront for the 1024-sphere scene, fused per-pixel
     # kernel for the 14-sphere demo configs
@@ -246,7 +249,7 @@ def main():
         sr.redraw(cam, stats=st, **opts_kw)
         st_acc["p"] += st.ms_trace_primary; st_acc["s"] += st.ms_trace_secondary
         st_acc["sh"] += st.ms_shadow; st_acc["c"] += st.ms_compose; st_acc["k"] += st.kernel_ms
-        st_acc["launches"] += 2 * (st.launches + (1 if world > 1 else 0))      # timed + instrumented pass
+        st_acc["launches"] += 2 * (st.launches + xl)                           # timed + instrumented pass
         st_acc["nodes"], st_acc["shadow"] = int(st.nodes), int(st.shadow_rays)
     barrier()
 
@@ -279,7 +282,7 @@ def main():
                     frame = sr.redraw(cam, stats=st, **opts_kw)
                 finally:
                     sr.r._h = old
-                e2e_launches += st.launches + 1
+                e2e_launches += st.launches + xl
                 if rank == 0:
                     host.copy_(frame, non_blocking=True)
                 torch.cuda.synchronize()
@@ -300,6 +303,7 @@ def main():
     e2e_ms = float(te.item())
     e2e_value = rays_per_frame / (e2e_ms * 1e-3) / 1e6
 
+    sr.close()                               # collective: unmap the peers' buffers, free this rank's
     if rank != 0:
         renderer.close()
         dist.barrier()
@@ -356,7 +360,11 @@ def main():
                    "scene": "synth1024 (numpy default_rng(1024), reference sort)" if scene != "demo" else "demo (main.js:107-163)",
                    "width": W, "height": H, "segs": segs, "spp": g * g, "n_spheres": cnt["n_spheres"],
                    "rays_per_frame": rays_per_frame, "kernel": "wavefront fp32" if use_wf else "per-pixel fp32 (AUTO, N <= 32)",
-                   "partition": "single GPU" if world == 1 else f"interleaved {sr.S}-row stripes + NCCL all-gather",
+                   "partition": "single GPU" if world == 1 else (
+                       f"interleaved {sr.S}-row stripes + " +
+                       ("peer-memory scatter kernel over NVLink (rtb_peer_scatter)" if sr.exchange == "p2p"
+                        else "NCCL all-gather + de-interleave kernel") +
+                       (f"; {sr.exchange_note}" if sr.exchange_note else "")),
                    "frames_in_flight": fif,
                    "l2": "per-frame working set (ray/node queues, ~2.7 GB) exceeds the 126 MB L2; no flush needed"},
         "roofline": roofline,

@@ -117,7 +117,8 @@ class RtbStats(C.Structure):
 
 # Every symbol include/rtb200.h declares; tests assert the built library exports all of them.
 EXPORTS = [
-    "rtb_init", "rtb_shutdown", "rtb_scene_create", "rtb_scene_destroy", "rtb_scene_h2d_bytes", "rtb_finish", "rtb_set_frames_in_flight", "rtb_copy_status_device", "rtb_render",
+    "rtb_init", "rtb_shutdown", "rtb_scene_create", "rtb_scene_destroy", "rtb_scene_h2d_bytes", "rtb_finish", "rtb_set_frames_in_flight", "rtb_copy_status_device",
+    "rtb_peer_alloc", "rtb_peer_open", "rtb_peer_close", "rtb_peer_free", "rtb_peer_scatter", "rtb_peer_signal", "rtb_peer_wait", "rtb_render",
     "rtb_render_device", "rtb_render_batch", "rtb_unstripe_device", "rtb_stripe_local_rows",
     "rtb_stripe_padded_rows", "rtb_default_opts", "rtb_last_error", "rtb_version",
     "rtb_abi_version", "rtb_device_info",
@@ -153,6 +154,17 @@ def load() -> C.CDLL:
     lib.rtb_scene_h2d_bytes.argtypes = [vp]; lib.rtb_scene_h2d_bytes.restype = C.c_uint64
     lib.rtb_finish.argtypes = [vp]; lib.rtb_finish.restype = C.c_int
     lib.rtb_set_frames_in_flight.argtypes = [C.c_int32]; lib.rtb_set_frames_in_flight.restype = C.c_int
+    u8p = C.POINTER(C.c_uint8)
+    vpp = C.POINTER(C.c_void_p)
+    lib.rtb_peer_alloc.argtypes = [C.c_uint64, vpp, u8p]; lib.rtb_peer_alloc.restype = C.c_int
+    lib.rtb_peer_open.argtypes = [u8p, vpp]; lib.rtb_peer_open.restype = C.c_int
+    lib.rtb_peer_close.argtypes = [vp]; lib.rtb_peer_close.restype = C.c_int
+    lib.rtb_peer_free.argtypes = [vp]; lib.rtb_peer_free.restype = C.c_int
+    lib.rtb_peer_scatter.argtypes = [vp, vpp, vpp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp,
+                                     C.c_uint32, C.c_uint32, C.c_uint32, vp]
+    lib.rtb_peer_scatter.restype = C.c_int
+    lib.rtb_peer_signal.argtypes = [vpp, C.c_int32, C.c_int32, C.c_uint32, C.c_uint32, vp]; lib.rtb_peer_signal.restype = C.c_int
+    lib.rtb_peer_wait.argtypes = [vp, C.c_int32, C.c_uint32, C.c_uint32, vp, vp]; lib.rtb_peer_wait.restype = C.c_int
     lib.rtb_copy_status_device.argtypes = [vp, vp, vp]; lib.rtb_copy_status_device.restype = C.c_int
     lib.rtb_render.argtypes = [vp, C.POINTER(RtbCamera), C.POINTER(RtbRenderOpts), vp, C.POINTER(RtbStats)]
     lib.rtb_render.restype = C.c_int

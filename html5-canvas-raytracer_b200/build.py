@@ -26,6 +26,7 @@ SOURCES = {
     "pixel_f64.cu": ["-fmad=false"],
     "pixel_f32.cu": [],
     "wavefront.cu": [],
+    "peer.cu": [],
 }
 HEADERS = ["rtb_device.cuh", "rtb_internal.h", "pixel_kernel.cuh", "pixel_launch.inl",
            os.path.join(INCLUDE, "rtb200.h")]

@@ -410,6 +410,7 @@ void rtb_shutdown(void) {
   cudaFree(g_rtb.d_frame[0]); cudaFree(g_rtb.d_frame[1]); cudaFree(g_rtb.d_counters);
   cudaFree(g_rtb.cached_arena);
   cudaFree(g_rtb.d_star);
+  cudaFree(g_rtb.d_peer_counter);
   if (g_rtb.h_stage) cudaFreeHost(g_rtb.h_stage);
   wf_free();
   (void)cudaGetLastError();

@@ -112,6 +112,7 @@ struct RtbGlobal {
   int frames_in_flight = 1;                   // 1 .. RTB_MAX_IN_FLIGHT (rtb_set_frames_in_flight)
   int next_slot = 0, last_slot = 0;
   unsigned long long* d_counters = nullptr;   // 3 x u64 for the pixel kernels
+  uint32_t* d_peer_counter = nullptr;         // last-block election words of rtb_peer_scatter
   char* cached_arena = nullptr;               // last destroyed scene's device arena, reused by the next create
   size_t cached_arena_bytes = 0;
   char* h_stage = nullptr;                    // pinned staging for scene uploads and per-camera tables

@@ -13,6 +13,7 @@ C ABI.  The partition arithmetic is pure Python so that it can be tested with gl
 """
 from __future__ import annotations
 
+import ctypes as C
 import os
 from typing import List, Sequence
 
@@ -73,15 +74,35 @@ def init_distributed(backend: str | None = None):
     return rank, local_rank, world
 
 
+class _DeviceBytes:
+    """A raw device allocation of the library, viewable as a torch tensor (__cuda_array_interface__)."""
+
+    def __init__(self, ptr: int, shape, typestr="|u1"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+# control block of the peer exchange, uint32 words; one row of RTB_MAX_PEERS words per frame slot
+_CTL_READY, _CTL_STATUS, _CTL_ACK, _CTL_TIMEOUT, _CTL_WORDS = 0, 64, 128, 192, 256
+_PEER_TIMEOUT_MS = 20000
+
+
 class StripedRenderer:
     """Row-stripe sharded redraw(): every rank ends up with the full framebuffer on its GPU.
 
-    Gather layout per rank: [padded_rows + 1][W][4] — the packed stripe rows plus one trailer row whose
-    first word is the rank's status (non-zero: its ray queues overflowed, the frame must be repeated).
-    Shipping the status inside the payload gives every rank the same verdict from the one collective."""
+    exchange = "p2p" (default on GPUs): each rank stores its packed stripe rows straight into every rank's
+    framebuffer over NVLink with one kernel of the library (rtb_peer_scatter: all-gather + de-interleave in
+    one pass, no collective library in the data path, nothing spins while holding SMs); sequence numbers
+    and per-rank status words travel in a small control block.  Buffers are shared with CUDA IPC handles
+    exchanged once over torch.distributed.
+    exchange = "nccl": `all_gather_into_tensor` of [padded_rows + 1][W][4] per rank — the packed stripe rows
+    plus one trailer row whose first word is the rank's status — followed by rtb_unstripe_device.
+    Either way a non-zero status word (that rank's ray queues overflowed) reaches every rank with the
+    frame, so all ranks take the same repeat decision without a second exchange.
+    "auto" tries p2p and falls back to nccl when the ranks cannot map each other's memory."""
 
     def __init__(self, renderer, width: int, height: int, rank: int, world: int,
-                 stripe_rows: int = DEFAULT_STRIPE_ROWS):
+                 stripe_rows: int = DEFAULT_STRIPE_ROWS, exchange: str = "auto"):
         import torch
 
         self.r, self.W, self.H = renderer, width, height
@@ -94,14 +115,112 @@ class StripedRenderer:
         self.dev = dev
         # MAX_IN_FLIGHT sets of everything: redraw_sequence keeps several frames in flight
         K = MAX_IN_FLIGHT
-        self.frames = [torch.empty((height, width, 4), dtype=torch.uint8, device=dev) for _ in range(K)]
-        self.frame = self.frames[0]
-        self.flags_host = [torch.zeros((max(world, 1),), dtype=torch.int32).pin_memory() for _ in range(K)]
+        self.flags_host = [torch.zeros((max(world, 1) + 1,), dtype=torch.int32).pin_memory() for _ in range(K)]
         self.status_dev = torch.zeros((K, 4), dtype=torch.int32, device=dev)      # world == 1: status words
         self._streams = None
+        self.exchange = "none"
+        self.exchange_note = ""
+        self._peer = None
         if world > 1:
             self.local = [torch.zeros((self.stride, width, 4), dtype=torch.uint8, device=dev) for _ in range(K)]
-            self.gathered = [torch.empty((world, self.stride, width, 4), dtype=torch.uint8, device=dev) for _ in range(K)]
+            if exchange not in ("auto", "p2p", "nccl"):
+                raise ValueError(f"exchange must be auto, p2p or nccl (got {exchange!r})")
+            if exchange in ("auto", "p2p"):
+                err = self._setup_p2p()
+                if err is None:
+                    self.exchange = "p2p"
+                elif exchange == "p2p":
+                    raise RuntimeError(f"peer-memory exchange unavailable: {err}")
+                else:
+                    self.exchange_note = f"p2p unavailable ({err})"
+            if self.exchange != "p2p":
+                self.exchange = "nccl"
+                self.gathered = [torch.empty((world, self.stride, width, 4), dtype=torch.uint8, device=dev) for _ in range(K)]
+        if self.exchange != "p2p":
+            self.frames = [torch.empty((height, width, 4), dtype=torch.uint8, device=dev) for _ in range(K)]
+        self.frame = self.frames[0]
+
+    # -- peer-memory exchange: set-up ----------------------------------------------------------------------
+    def _setup_p2p(self):
+        """Allocate this rank's framebuffers + control block in the library, swap IPC handles, map the
+        peers'.  Returns None on success, else a one-line reason — the same on every rank."""
+        import torch
+        import torch.distributed as dist
+
+        K, world = MAX_IN_FLIGHT, self.world
+        if world > 16 or self.W % 4 != 0:
+            return "needs world <= 16 and a width that is a multiple of 4"
+        frame_bytes = self.H * self.W * 4
+        own = {"frames": C.c_void_p(), "ctl": C.c_void_p()}
+        handles = {k: (C.c_uint8 * 64)() for k in own}
+        err = None
+        try:
+            A.check(self.lib.rtb_peer_alloc(K * frame_bytes, C.byref(own["frames"]), handles["frames"]))
+            A.check(self.lib.rtb_peer_alloc(_CTL_WORDS * 4, C.byref(own["ctl"]), handles["ctl"]))
+        except A.RtbError as e:
+            err = str(e)
+        mine = None if err else (bytes(handles["frames"]), bytes(handles["ctl"]))
+        everyone = [None] * world
+        dist.all_gather_object(everyone, mine)
+        if any(h is None for h in everyone):
+            err = err or "a peer could not allocate its buffers"
+        bases = {"frames": [0] * world, "ctl": [0] * world}
+        opened = []
+        if err is None:
+            for p in range(world):
+                for k, key in enumerate(("frames", "ctl")):
+                    if p == self.rank:
+                        bases[key][p] = own[key].value
+                        continue
+                    ptr = C.c_void_p()
+                    h = (C.c_uint8 * 64).from_buffer_copy(everyone[p][k])
+                    rc = self.lib.rtb_peer_open(h, C.byref(ptr))
+                    if rc != 0:
+                        err = f"rank {self.rank} cannot map rank {p}: {self.lib.rtb_last_error().decode()}"
+                        break
+                    opened.append(ptr.value)
+                    bases[key][p] = ptr.value
+                if err:
+                    break
+        ok = torch.tensor([0 if err else 1], dtype=torch.int32, device=self.dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            for ptr in opened:
+                self.lib.rtb_peer_close(C.c_void_p(ptr))
+            dist.barrier()
+            for key in own:
+                if own[key].value:
+                    self.lib.rtb_peer_free(own[key])
+            return err or "a peer could not map this rank's buffers"
+        VP = C.c_void_p * world
+        self._peer = {
+            "own": own, "opened": opened,
+            "frames": [VP(*[bases["frames"][p] + k * frame_bytes for p in range(world)]) for k in range(K)],
+            "ctl": VP(*bases["ctl"]),
+            "ctl_base": own["ctl"].value,
+            "seq": 0, "slot_seq": [0] * K, "unacked": [0] * K,
+        }
+        self.frames = [torch.as_tensor(_DeviceBytes(own["frames"].value + k * frame_bytes, (self.H, self.W, 4)),
+                                       device=self.dev) for k in range(K)]
+        self._ctl = torch.as_tensor(_DeviceBytes(own["ctl"].value, (_CTL_WORDS,), "<i4"), device=self.dev)
+        return None
+
+    def close(self):
+        """Unmap the peers' buffers and free this rank's (collective: every rank calls it)."""
+        import torch
+        import torch.distributed as dist
+
+        if self._peer is None:
+            return
+        torch.cuda.synchronize()
+        dist.barrier()
+        for ptr in self._peer["opened"]:
+            self.lib.rtb_peer_close(C.c_void_p(ptr))
+        dist.barrier()
+        for key in ("frames", "ctl"):
+            self.lib.rtb_peer_free(self._peer["own"][key])
+        self._peer = None
+        self.frames = []
 
     # -- building blocks (everything is enqueued on the CURRENT torch stream) --------------------------
     def _enqueue_render(self, camera, slot, stats, kw):
@@ -130,38 +249,77 @@ class StripedRenderer:
         A.check(self.lib.rtb_unstripe_device(self.gathered[slot].data_ptr(), self.frames[slot].data_ptr(), self.W,
                                              self.H, self.S, self.world, self.stride, A.stream_arg(stream)))
         flags = self.gathered[slot][:, self.padded, 0, :].contiguous().view(torch.int32).view(-1)
-        self.flags_host[slot].copy_(flags, non_blocking=True)
+        self.flags_host[slot][:self.world].copy_(flags, non_blocking=True)
 
-    def _enqueue_frame(self, camera, slot, kw):
-        """Render (+ gather + de-interleave) of one frame into self.frames[slot]; status words to the host."""
-        self._enqueue_render(camera, slot, None, kw)
-        if self.world > 1:
+    def _enqueue_release(self, slot):
+        """p2p: tell every peer that this rank no longer reads framebuffer `slot` (its previous frame)."""
+        import torch
+
+        P = self._peer
+        if P["unacked"][slot]:
+            st = A.stream_arg(torch.cuda.current_stream().cuda_stream)
+            A.check(self.lib.rtb_peer_signal(P["ctl"], self.world, self.rank, _CTL_ACK + 16 * slot, P["unacked"][slot], st))
+            P["unacked"][slot] = 0
+
+    def _enqueue_scatter(self, slot):
+        """p2p: wait until every peer has released framebuffer `slot`, store this rank's rows into all of
+        them, wait until every rank's rows of this frame have arrived here."""
+        import torch
+
+        P = self._peer
+        st = A.stream_arg(torch.cuda.current_stream().cuda_stream)
+        P["seq"] += 1
+        seq, prev = P["seq"], P["slot_seq"][slot]
+        ctl = P["ctl_base"]
+        tflag = C.c_void_p(ctl + 4 * _CTL_TIMEOUT)
+        if prev:
+            A.check(self.lib.rtb_peer_wait(C.c_void_p(ctl + 4 * (_CTL_ACK + 16 * slot)), self.world, prev,
+                                           _PEER_TIMEOUT_MS, tflag, st))
+        A.check(self.lib.rtb_peer_scatter(C.c_void_p(self.local[slot].data_ptr()), P["frames"][slot], P["ctl"], self.W,
+                                          self.H, self.S, self.rank, self.world,
+                                          C.c_void_p(self.local[slot][self.padded].data_ptr()),
+                                          _CTL_READY + 16 * slot, _CTL_STATUS + 16 * slot, seq, st))
+        A.check(self.lib.rtb_peer_wait(C.c_void_p(ctl + 4 * (_CTL_READY + 16 * slot)), self.world, seq,
+                                       _PEER_TIMEOUT_MS, tflag, st))
+        P["slot_seq"][slot] = seq
+        P["unacked"][slot] = seq
+        s0 = _CTL_STATUS + 16 * slot
+        self.flags_host[slot][:self.world].copy_(self._ctl[s0:s0 + self.world], non_blocking=True)
+        self.flags_host[slot][self.world:].copy_(self._ctl[_CTL_TIMEOUT:_CTL_TIMEOUT + 1], non_blocking=True)
+
+    def _enqueue_frame(self, camera, slot, kw, stats=None):
+        """Render + exchange of one frame into self.frames[slot]; status words to the host."""
+        if self.exchange == "p2p":
+            self._enqueue_release(slot)
+        self._enqueue_render(camera, slot, stats, kw)
+        if self.exchange == "p2p":
+            self._enqueue_scatter(slot)
+        elif self.exchange == "nccl":
             self._enqueue_gather(slot).wait()             # stream-level wait, the host does not block
             self._enqueue_unstripe(slot)
         else:
-            self.flags_host[slot].copy_(self.status_dev[slot, :1], non_blocking=True)
+            self.flags_host[slot][:1].copy_(self.status_dev[slot, :1], non_blocking=True)
+
+    def _frame_ok(self, slot) -> bool:
+        """Host side, after the frame's stream work has completed: did every rank render it validly?"""
+        f = self.flags_host[slot]
+        if self.exchange == "p2p" and int(f[self.world]) != 0:
+            raise RuntimeError("peer exchange timed out: a rank stopped publishing frames")
+        return not bool(f[:max(self.world, 1)].any())
 
     # -- one frame (latency mode) ----------------------------------------------------------------------
     def redraw(self, camera, stats=None, **kw):
-        """Render this rank's stripes, all-gather, de-interleave.  Returns the device framebuffer.
+        """Render this rank's stripes, exchange, return the device framebuffer (valid until the next call).
         Everything is only ENQUEUED; the host waits once.  If any rank's ray queues overflowed, every
-        rank sees that in the gathered status words and repeats the frame (the library has shrunk the
-        offending rank's bands, deterministically)."""
+        rank sees that in the status words and repeats the frame (the library has shrunk the offending
+        rank's bands, deterministically)."""
         import torch
 
         while True:
-            if stats is not None:
-                self._enqueue_render(camera, 0, stats, kw)
-                if self.world > 1:
-                    self._enqueue_gather(0).wait()
-                    self._enqueue_unstripe(0)
-                else:
-                    self.flags_host[0].copy_(self.status_dev[0, :1], non_blocking=True)
-            else:
-                self._enqueue_frame(camera, 0, kw)
+            self._enqueue_frame(camera, 0, kw, stats)
             torch.cuda.current_stream().synchronize()
             self.r.finish()                               # clears the library's pending state (already complete)
-            if not bool(self.flags_host[0].any()):
+            if self._frame_ok(0):
                 self.frame = self.frames[0]
                 return self.frame
 
@@ -200,7 +358,7 @@ class StripedRenderer:
                 j = inflight.pop(0)
                 jslot = j % depth
                 done[jslot].synchronize()                 # the host waits for frame j only
-                if bool(self.flags_host[jslot].any()):    # same words on every rank: same decision everywhere
+                if not self._frame_ok(jslot):             # same words on every rank: same decision everywhere
                     repeats += 1
                     for st in self._streams:
                         st.synchronize()

@@ -231,6 +231,39 @@ int rtb_render_batch(rtb_scene_t scene, const RtbCamera* cams, int32_t nframes,
 int rtb_unstripe_device(const void* d_gathered, void* d_frame, int32_t width, int32_t height,
                         int32_t stripe_rows, int32_t stripe_world, int32_t rank_stride_rows, void* cuda_stream);
 
+/* ---- framebuffer exchange over peer memory (NVLink / NVSwitch), multi-GPU mode without a collective ----
+ * One process per GPU.  Buffers are cudaMalloc'ed by the library and shared with CUDA IPC handles, which
+ * the host layer exchanges once (torch.distributed all_gather_object, MPI, a pipe ...).
+ *   rtb_peer_alloc   allocate + zero a shareable device buffer, return its 64-byte IPC handle
+ *   rtb_peer_open    map another process's buffer (peer access is enabled on first use)
+ *   rtb_peer_close / rtb_peer_free
+ * Per rank: K framebuffers (W*H*4 bytes) and one control block of uint32 words, all opened by all peers.
+ *   rtb_peer_scatter enqueue ONE kernel that stores this rank's packed stripe rows (rtb_render_device with
+ *                    out_packed = 1) into every rank's framebuffer at their final rows, then writes this
+ *                    rank's status word to ctl[status_offset + rank] and `seq` to ctl[ready_offset + rank]
+ *                    of every peer (release order: a peer that sees seq also sees the rows and the status).
+ *                    peer_frames / peer_ctl are HOST arrays of `stripe_world` device pointers, own included.
+ *   rtb_peer_wait    enqueue a one-warp kernel that holds the stream until n consecutive uint32 words have
+ *                    all reached `value` (signed distance; sequence numbers only grow).  After timeout_ms
+ *                    it gives up and sets *d_timeout_flag_u32 = 1 instead of hanging the GPU.
+ *   rtb_peer_signal  enqueue: ctl[word_offset + rank] = value on every peer (e.g. "I am done reading
+ *                    framebuffer k": the credit a producer waits for before overwriting it).
+ * Replaces, for the multi-GPU mode, the ncclAllGather + rtb_unstripe_device pair. */
+#define RTB_MAX_PEERS 16
+#define RTB_PEER_HANDLE_BYTES 64
+int rtb_peer_alloc(uint64_t bytes, void** d_ptr, uint8_t* handle64);
+int rtb_peer_open(const uint8_t* handle64, void** d_ptr);
+int rtb_peer_close(void* d_ptr);
+int rtb_peer_free(void* d_ptr);
+int rtb_peer_scatter(const void* d_local_packed, void* const* peer_frames, void* const* peer_ctl, int32_t width,
+                     int32_t height, int32_t stripe_rows, int32_t stripe_rank, int32_t stripe_world,
+                     const void* d_status_u32, uint32_t ready_offset, uint32_t status_offset, uint32_t seq,
+                     void* cuda_stream);
+int rtb_peer_signal(void* const* peer_ctl, int32_t world, int32_t rank, uint32_t word_offset, uint32_t value,
+                    void* cuda_stream);
+int rtb_peer_wait(const void* d_words_u32, int32_t n, uint32_t value, uint32_t timeout_ms, void* d_timeout_flag_u32,
+                  void* cuda_stream);
+
 /* Number of rows rank `stripe_rank` owns / the padded per-rank row count used by the gather. */
 int32_t rtb_stripe_local_rows(int32_t height, int32_t stripe_rows, int32_t stripe_rank,
                               int32_t stripe_world);

@@ -13,13 +13,14 @@ os.environ["NCCL_DEBUG"] = "WARN"
 rank, local_rank, world = mg.init_distributed()
 torch.cuda.set_device(local_rank)
 W, H = 640, 362
+XCH = os.environ.get("RTB_EXCHANGE", "auto")
 objs = rt.scenes.synth_objects(256, 11)
 demo = rt.scenes.demo_objects()
 cams = rt.scenes.orbit_cameras(W, H, nframes=12)[:9]
 kw = dict(segs=8, kernel=rt.RTB_KERNEL_WAVEFRONT)
 with rt.Renderer(objs, device=local_rank) as r:
     refs = [r.redraw(c, **kw) for c in cams]                       # single-GPU frames (every rank computes them)
-    sr = mg.StripedRenderer(r, W, H, rank, world)
+    sr = mg.StripedRenderer(r, W, H, rank, world, exchange=XCH)
     ok = True
     for ci, (c, ref) in enumerate(zip(cams, refs)):
         f = sr.redraw(c, **kw).cpu().numpy()
@@ -50,25 +51,28 @@ with rt.Renderer(objs, device=local_rank) as r:
         if saved:
             os.environ["RTB_WF_CAP_NODES"] = saved
     with rt.Renderer(demo, device=local_rank) as r2:
-        sr2 = mg.StripedRenderer(r2, W, H, rank, world)
+        sr2 = mg.StripedRenderer(r2, W, H, rank, world, exchange=XCH)
         f = sr2.redraw(cams[1], **kw).cpu().numpy()
         s2 = bool(np.array_equal(f, drefs[1]))
         if not s2:
             print(f"rank {rank}: forced-overflow single frame differs", flush=True)
         ok &= s2
+        sr2.close()
     with rt.Renderer(demo, device=local_rank) as r3:
-        sr3 = mg.StripedRenderer(r3, W, H, rank, world)
+        sr3 = mg.StripedRenderer(r3, W, H, rank, world, exchange=XCH)
         got2 = {}
         rep2 = sr3.redraw_sequence(cams, on_frame=lambda i, fr: got2.__setitem__(i, fr.cpu().numpy().copy()), **kw)
         s3 = [bool(np.array_equal(got2[i], drefs[i])) for i in range(len(cams))]
         if not all(s3) or rep2 == 0:
             print(f"rank {rank}: forced-overflow sequence ok={s3} repeats={rep2}", flush=True)
         ok &= all(s3) and rep2 > 0
+        sr3.close()
     os.environ.pop("RTB_WF_CAP_NODES", None)
+    sr.close()
     t = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print(f"mgpu_check world={world}: {'OK' if int(t.item()) else 'MISMATCH'} (sequence repeats without/with forced overflow: {rep}/{rep2})")
+        print(f"mgpu_check world={world} exchange={sr.exchange} {sr.exchange_note}: {'OK' if int(t.item()) else 'MISMATCH'} (sequence repeats without/with forced overflow: {rep}/{rep2})")
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)
