@@ -43,7 +43,7 @@ struct WfBuffers {
   WfCounters* ctr;
 };
 
-constexpr int RTB_MAX_IN_FLIGHT = 4;   // workspace slots: asynchronous wavefront frames that may overlap
+constexpr int RTB_MAX_IN_FLIGHT = 8;   // workspace slots: asynchronous wavefront frames that may overlap
 
 struct RtbScene_ {
   int n_spheres = 0, n_textures = 0, n_lights = 0;

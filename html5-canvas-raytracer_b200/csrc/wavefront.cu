@@ -33,6 +33,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <vector>
+#include <map>
+#include <utility>
 #include "rtb_internal.h"
 #include "pixel_kernel.cuh"   // primary_ray<>
 
@@ -64,8 +66,6 @@ struct WfParams {
   uint32_t n_sub;             // band_rows * W * spp  == number of level-1 nodes
   int32_t spp;                // g*g
   int32_t aligned4;           // W % 4 == 0 and output 16-byte aligned: uint4 stores
-  int32_t team_mode;          // 0 = whole-table chunks only, 1 = auto (team chunks for small levels and tails), 2 = team only
-  uint32_t team_rounds;       // auto: levels shorter than this many whole-table rounds run in team chunks throughout
   int32_t fixed_r;            // 0: rays per lane from the cost model; 1/2/3: always R, R/2, R/4 and no guided tail
 };
 
@@ -80,7 +80,6 @@ static_assert(RTB_WF_GROUP % WF_GROUP == 0, "table padding must be a multiple of
 constexpr int R_SHARED = 8;              // rays per lane, shared-origin sweeps (primary, shadow)
 constexpr int R_GENERAL = 4;             // rays per lane, general sweep (reflect / refract rays)
 constexpr unsigned long long KEY_NONE = 0x7f800000ffffffffull;   // t = +inf, no sphere
-constexpr int R_TEAM = 4;                // rays per lane of a team chunk (see trace_team)
 constexpr int WF_WARPS = WF_THREADS / 32;
 
 RTB_DEVINL uint32_t lanemask_lt() { uint32_t m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
@@ -116,6 +115,17 @@ RTB_DEVINL uint32_t next_chunk(uint32_t* counter, uint32_t lane) {
   uint32_t c = 0;
   if (lane == 0) c = atomicAdd(counter, 1u);
   return __shfl_sync(0xffffffffu, c, 0);
+}
+
+// First claim of a persistent CTA: eight consecutive chunks at once, one per warp.  A level that does
+// not fill the grid is then worked on by ceil(chunks / 8) CTAs with all their warps busy, and the other
+// CTAs leave immediately, instead of every CTA staying resident for the sake of one or two busy warps —
+// which matters when the kernels of several frames share the GPU.  (Contains a CTA barrier.)
+RTB_DEVINL uint32_t cta_claim(uint32_t* counter) {
+  __shared__ uint32_t s_first;
+  if (threadIdx.x == 0) s_first = atomicAdd(counter, (uint32_t)WF_WARPS);
+  __syncthreads();
+  return s_first + (threadIdx.x >> 5);
 }
 
 RTB_DEVINL float2 f2(float a, float b) { return make_float2(a, b); }
@@ -535,29 +545,18 @@ RTB_DEVINL WfRay ray_record(const WfParams& P, uint32_t node, bool active, float
   return r;
 }
 
-// CTA_FETCH: the CTA takes eight consecutive chunks per fetch (one per warp) so that its warps reach
-// the end of the range together — required when a team phase (CTA-wide barriers) follows.
-template <bool PRIMARY, int R, bool CTA_FETCH>
-RTB_DEVINL void trace_chunks(const WfParams& P, uint32_t* work, const float4* __restrict__ tab, uint32_t begin,
-                             uint32_t end, uint32_t lane, unsigned long long& my_nodes) {
+// `first` is the warp's first chunk, claimed for the whole CTA at once (cta_claim); the following ones
+// are pulled per warp.
+template <bool PRIMARY, int R>
+RTB_DEVINL void trace_chunks(const WfParams& P, uint32_t* work, uint32_t first, const float4* __restrict__ tab,
+                             uint32_t begin, uint32_t end, uint32_t lane, unsigned long long& my_nodes) {
   const int n_pad = P.n_pad;
   const float eps = P.sc.eps;
   constexpr uint32_t CHUNK = 32u * R;
-  __shared__ uint32_t s_first;
 
-  for (;;) {
-    uint32_t c;
-    if (CTA_FETCH) {
-      __syncthreads();
-      if (threadIdx.x == 0) s_first = atomicAdd(work, (uint32_t)WF_WARPS);
-      __syncthreads();
-      if ((uint64_t)begin + (uint64_t)s_first * CHUNK >= end) break;
-      c = s_first + (threadIdx.x >> 5);
-    } else {
-      c = next_chunk(work, lane);
-    }
+  for (uint32_t c = first;; c = next_chunk(work, lane)) {
     const uint64_t base = (uint64_t)begin + (uint64_t)c * CHUNK;
-    if (base >= end) { if (CTA_FETCH) continue; else break; }
+    if (base >= end) break;
     float a[R][3], b[R][3];          // PRIMARY: a = -dir;  general: a = u, b = v (basis completing dir)
     float nku[R], nkv[R];            // general: -(u.org), -(v.org)
     uint32_t nodes[R];
@@ -589,105 +588,31 @@ RTB_DEVINL void trace_chunks(const WfParams& P, uint32_t* work, const float4* __
   }
 }
 
-// TEAM mode: the whole CTA works on ONE chunk of 32 x R_TEAM rays.  Every warp sweeps its own eighth of
-// the sphere table for all of the chunk's rays, the closest-hit keys are min-reduced through shared
-// memory (the key order is total, so the result is the one a single sweep would find), and warps
-// 0..R_TEAM-1 then run process_hit with one ray per lane.  A chunk lasts an eighth as long as a
-// whole-table chunk and occupies all four schedulers of the SM evenly, which is what small levels
-// (deep recursion, one stripe set of a multi-GPU frame) and the tail of large ones need: the launch
-// ends within one short chunk of the moment the work runs out.
-template <bool PRIMARY>
-RTB_DEVINL void trace_team(const WfParams& P, uint32_t* work, const float4* __restrict__ tab, uint32_t begin,
-                           uint32_t end, unsigned long long& my_nodes) {
-  constexpr int R = R_TEAM;
-  constexpr uint32_t CHUNK = 32u * R;
-  __shared__ unsigned long long s_best[WF_WARPS][CHUNK];
-  __shared__ uint32_t s_chunk[2];
-  const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
-  const float eps = P.sc.eps;
-  // slice of the table in sweep groups
-  const int groups = P.n_pad / WF_GROUP;
-  const int j_begin = (int)((w * (uint32_t)groups) / WF_WARPS) * WF_GROUP;
-  const int j_end = (int)(((w + 1u) * (uint32_t)groups) / WF_WARPS) * WF_GROUP;
-
-  if (threadIdx.x == 0) s_chunk[0] = atomicAdd(work, 1u);
-  for (uint32_t it = 0;; it++) {
-    __syncthreads();                                       // chunk id visible, s_best free again
-    const uint64_t base = (uint64_t)begin + (uint64_t)s_chunk[it & 1u] * CHUNK;
-    if (base >= end) break;
-    float a[R][3], b[R][3], nku[R], nkv[R];
-    uint32_t nodes[R];
-    int self[R];
-    bool active[R];
-    unsigned long long best[R];
-#pragma unroll
-    for (int q = 0; q < R; q++) {
-      const uint32_t node = (uint32_t)base + (uint32_t)q * 32u + lane;
-      nodes[q] = node;
-      active[q] = node < end;
-      a[q][0] = a[q][1] = a[q][2] = 0.f;
-      b[q][0] = b[q][1] = b[q][2] = 0.f;
-      nku[q] = 3.0e18f; nkv[q] = 0.f;
-      self[q] = -1;
-      if (active[q]) ray_setup<PRIMARY>(P, node, a[q], b[q], nku[q], nkv[q], self[q]);
-    }
-    if (PRIMARY) sweep_primary<R>(tab, P.primary_x, j_begin, j_end, a, active, best, eps);
-    else sweep_general<R>(tab, P.geom, P.b.ray_o, P.b.ray_d, j_begin, j_end, a, b, nku, nkv, nodes, self, active, best, eps);
-#pragma unroll
-    for (int q = 0; q < R; q++) s_best[w][q * 32 + lane] = best[q];
-    __syncthreads();
-    if (threadIdx.x == 0) s_chunk[(it + 1u) & 1u] = atomicAdd(work, 1u);   // slot last read before the barrier above
-    if (w < (uint32_t)R) {
-      const uint32_t slot = w * 32u + lane;
-      unsigned long long key = s_best[0][slot];
-#pragma unroll
-      for (int v = 1; v < WF_WARPS; v++) { const unsigned long long k2 = s_best[v][slot]; if (k2 < key) key = k2; }
-      float nd[3] = {0.f, 0.f, 0.f};
-      bool act = false;
-#pragma unroll
-      for (int q = 0; q < R; q++)
-        if ((uint32_t)q == w) { nd[0] = a[q][0]; nd[1] = a[q][1]; nd[2] = a[q][2]; act = active[q]; }
-      if (act) my_nodes++;
-      process_hit(P, ray_record<PRIMARY>(P, (uint32_t)base + slot, act, nd[0], nd[1], nd[2]), key, lane);
-    }
-  }
-}
-
 template <bool PRIMARY>
 __global__ void __launch_bounds__(WF_THREADS, WF_MIN_CTAS)
 wf_trace_kernel(const __grid_constant__ WfParams P, int level) {
   constexpr int RB = PRIMARY ? R_SHARED : R_GENERAL;
   extern __shared__ float4 tab[];
   const int n = P.sc.n_spheres, n_pad = P.n_pad;
-  {
-    const float4* src = PRIMARY ? P.primary_tab : P.geom_tab;
-    for (int i = threadIdx.x; i < n_pad; i += blockDim.x) tab[i] = src[i];
-  }
-  __syncthreads();
   uint32_t begin, end;
   level_range(P, level, begin, end);
   const uint32_t lane = threadIdx.x & 31u;
   unsigned long long my_nodes = 0;
   uint32_t* wa = &P.b.ctr->work_trace[level];
   uint32_t* wt = &P.b.ctr->work_trace_tail[level];
-  if (P.team_mode == 0) {
-    const int r = P.fixed_r ? (RB >> (P.fixed_r - 1)) : pick_rays_per_lane(end - begin, RB, PRIMARY ? 9u : 20u);
-    const uint32_t split = P.fixed_r ? end : end - tail_rays(end - begin, r, RB / 4);
-    if (r == RB) trace_chunks<PRIMARY, RB, false>(P, wa, tab, begin, split, lane, my_nodes);
-    else if (r == RB / 2) trace_chunks<PRIMARY, RB / 2, false>(P, wa, tab, begin, split, lane, my_nodes);
-    else trace_chunks<PRIMARY, RB / 4, false>(P, wa, tab, begin, split, lane, my_nodes);
-    if (split < end) trace_chunks<PRIMARY, RB / 4, false>(P, wt, tab, split, end, lane, my_nodes);
-  } else {
-    // whole-table chunks for the bulk of a large level, team chunks for its last half round (CTAs leave
-    // the bulk phase up to one round apart) and for small levels altogether
-    const uint32_t count = end - begin;
-    const uint32_t cta_round = (uint32_t)WF_WARPS * 32u * (uint32_t)RB;        // rays per CTA fetch
-    const uint64_t round = (uint64_t)gridDim.x * cta_round;                    // rays per round of the grid
-    uint32_t n_big = 0;
-    if (P.team_mode == 1 && (uint64_t)count >= (uint64_t)P.team_rounds * round)
-      n_big = (uint32_t)(((uint64_t)count - round / 2u) / cta_round) * cta_round;
-    if (n_big) trace_chunks<PRIMARY, RB, true>(P, wa, tab, begin, begin + n_big, lane, my_nodes);
-    trace_team<PRIMARY>(P, wt, tab, begin + n_big, end, my_nodes);
+  const int r = P.fixed_r ? (RB >> (P.fixed_r - 1)) : pick_rays_per_lane(end - begin, RB, PRIMARY ? 9u : 20u);
+  const uint32_t split = P.fixed_r ? end : end - tail_rays(end - begin, r, RB / 4);
+  const uint32_t first = cta_claim(wa);
+  // a CTA whose claim lies beyond the level has nothing to do: leave at once (the slot goes to the
+  // kernels of the other frames in flight) without even loading the table
+  if ((uint64_t)begin + (uint64_t)(first - (threadIdx.x >> 5)) * (32u * (uint32_t)r) < split || split < end) {
+    const float4* src = PRIMARY ? P.primary_tab : P.geom_tab;
+    for (int i = threadIdx.x; i < n_pad; i += blockDim.x) tab[i] = src[i];
+    __syncthreads();
+    if (r == RB) trace_chunks<PRIMARY, RB>(P, wa, first, tab, begin, split, lane, my_nodes);
+    else if (r == RB / 2) trace_chunks<PRIMARY, RB / 2>(P, wa, first, tab, begin, split, lane, my_nodes);
+    else trace_chunks<PRIMARY, RB / 4>(P, wa, first, tab, begin, split, lane, my_nodes);
+    if (split < end) trace_chunks<PRIMARY, RB / 4>(P, wt, next_chunk(wt, lane), tab, split, end, lane, my_nodes);
   }
   // stats
   for (int o2 = 16; o2 > 0; o2 >>= 1) my_nodes += __shfl_down_sync(0xffffffffu, my_nodes, o2);
@@ -704,16 +629,16 @@ wf_trace_kernel(const __grid_constant__ WfParams P, int level) {
 // window along the reference's own ray (from hit.p toward the light): t = light_len - s.
 template <int R>
 RTB_DEVINL void shadow_chunks(const WfParams& P, int k, const float4* __restrict__ tab, uint32_t first,
-                              uint32_t count, uint32_t* work, uint32_t lane, unsigned long long& my_rays,
-                              unsigned long long& my_tests) {
+                              uint32_t count, uint32_t* work, uint32_t first_chunk, uint32_t lane,
+                              unsigned long long& my_rays, unsigned long long& my_tests) {
   const int n = P.sc.n_spheres, n_pad = P.n_pad;
   const float4* __restrict__ exact = P.light_x[k];
   const float eps = P.sc.eps;
   const float lx = P.sc.lights[k][0], ly = P.sc.lights[k][1], lz = P.sc.lights[k][2];
   constexpr uint32_t CHUNK = 32u * R;
 
-  for (;;) {
-    const uint64_t base = (uint64_t)first + (uint64_t)next_chunk(work, lane) * CHUNK;
+  for (uint32_t c = first_chunk;; c = next_chunk(work, lane)) {
+    const uint64_t base = (uint64_t)first + (uint64_t)c * CHUNK;
     if (base >= count) break;
     uint32_t node[R];
     int hit_i[R];
@@ -815,8 +740,6 @@ __global__ void __launch_bounds__(WF_THREADS, WF_MIN_CTAS)
 wf_shadow_kernel(const __grid_constant__ WfParams P, int k, int phase) {
   extern __shared__ float4 tab[];
   const int n_pad = P.n_pad;
-  for (int i = threadIdx.x; i < n_pad; i += blockDim.x) tab[i] = P.light_tab[k][i];
-  __syncthreads();
   uint32_t first = 0, count = *((volatile uint32_t*)&P.b.ctr->sq_count[k]);
   uint32_t* work = &P.b.ctr->work_shadow[k];
   if (phase == 1) { count = *((volatile uint32_t*)&P.b.ctr->sq_snap0); work = &P.b.ctr->work_shadow_early; }
@@ -826,10 +749,16 @@ wf_shadow_kernel(const __grid_constant__ WfParams P, int k, int phase) {
   uint32_t* work_tail = (phase == 1) ? &P.b.ctr->work_shadow_early_tail : &P.b.ctr->work_shadow_tail[k];
   const int r = P.fixed_r ? (R_SHARED >> (P.fixed_r - 1)) : pick_rays_per_lane(count - first, R_SHARED, 9u);
   const uint32_t split = P.fixed_r ? count : count - tail_rays(count - first, r, R_SHARED / 4);
-  if (r == R_SHARED) shadow_chunks<R_SHARED>(P, k, tab, first, split, work, lane, my_rays, my_tests);
-  else if (r == R_SHARED / 2) shadow_chunks<R_SHARED / 2>(P, k, tab, first, split, work, lane, my_rays, my_tests);
-  else shadow_chunks<R_SHARED / 4>(P, k, tab, first, split, work, lane, my_rays, my_tests);
-  if (split < count) shadow_chunks<R_SHARED / 4>(P, k, tab, split, count, work_tail, lane, my_rays, my_tests);
+  const uint32_t fc = cta_claim(work);
+  if ((uint64_t)first + (uint64_t)(fc - (threadIdx.x >> 5)) * (32u * (uint32_t)r) < split || split < count) {
+    for (int i = threadIdx.x; i < n_pad; i += blockDim.x) tab[i] = P.light_tab[k][i];
+    __syncthreads();
+    if (r == R_SHARED) shadow_chunks<R_SHARED>(P, k, tab, first, split, work, fc, lane, my_rays, my_tests);
+    else if (r == R_SHARED / 2) shadow_chunks<R_SHARED / 2>(P, k, tab, first, split, work, fc, lane, my_rays, my_tests);
+    else shadow_chunks<R_SHARED / 4>(P, k, tab, first, split, work, fc, lane, my_rays, my_tests);
+    if (split < count)
+      shadow_chunks<R_SHARED / 4>(P, k, tab, split, count, work_tail, next_chunk(work_tail, lane), lane, my_rays, my_tests);
+  }
   for (int o2 = 16; o2 > 0; o2 >>= 1) {
     my_rays += __shfl_down_sync(0xffffffffu, my_rays, o2);
     my_tests += __shfl_down_sync(0xffffffffu, my_tests, o2);
@@ -1086,29 +1015,27 @@ int wf_render(RtbScene_* s, const RtbCamera* cam, const DevFrameT<float>& fr32, 
   P.spp = spp;
   P.aligned4 = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_out) & 15u) == 0);
   {
-    // chunk scheduling of the trace kernels; RTB_WF_TEAM / RTB_WF_TEAM_ROUNDS override (experiments)
-    static int team_mode = -1, team_rounds = 2;
-    if (team_mode < 0) {
-      const char* e = getenv("RTB_WF_TEAM");
-      team_mode = e ? std::max(0, std::min(2, atoi(e))) : 0;
-      if (const char* r = getenv("RTB_WF_TEAM_ROUNDS")) team_rounds = std::max(1, atoi(r));
-    }
     static int fixed_r = -1;
     if (fixed_r < 0) { const char* e = getenv("RTB_WF_FIXED_R"); fixed_r = e ? std::max(0, std::min(3, atoi(e))) : 0; }
     // Three or more frames in flight: other frames' kernels fill this frame's tails, so the chunk size
     // that is cheapest per ray wins over the one that ends a lone launch soonest (measured, 1/8 of a 4K
     // frame per GPU: 1.37 -> 1.28 ms per frame).
     P.fixed_r = fixed_r ? fixed_r : (async && g_rtb.frames_in_flight >= 3 ? 1 : 0);
-    P.team_mode = team_mode;
-    P.team_rounds = (uint32_t)team_rounds;
   }
 
   // persistent grids: as many CTAs as fit, per kernel
+  // (the occupancy query costs ~10 us of host time per call: remembered per kernel and table size)
+  static std::map<std::pair<const void*, size_t>, int> occupancy;
   auto grid_for = [&](const void* fn, size_t sm) -> int {
-    int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, WF_THREADS, sm);
-    if (per_sm < 1) per_sm = 1;
-    return per_sm * g_rtb.sm_count;
+    const auto key = std::make_pair(fn, sm);
+    auto it = occupancy.find(key);
+    if (it == occupancy.end()) {
+      int per_sm = 0;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, WF_THREADS, sm);
+      if (per_sm < 1) per_sm = 1;
+      it = occupancy.emplace(key, per_sm).first;
+    }
+    return it->second * g_rtb.sm_count;
   };
   if (smem > 48 * 1024) {
     RTB_CUDA(cudaFuncSetAttribute(wf_trace_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

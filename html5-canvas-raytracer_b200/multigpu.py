@@ -23,9 +23,9 @@ from . import _abi as A
 from .scene import make_opts
 
 DEFAULT_STRIPE_ROWS = 4
-MAX_IN_FLIGHT = 4            # = RTB_MAX_IN_FLIGHT of the library
-DEFAULT_IN_FLIGHT = 3        # frames redraw_sequence keeps in flight (measured: 1.67 / 1.41 / 1.28 / 1.25 ms per
-                             # 1/8-frame for 1 / 2 / 3 / 4 on one B200)     # 2160 rows / 4 = 540 stripes: per-rank row counts differ by < 1.5 % at 8 ranks
+MAX_IN_FLIGHT = 8            # = RTB_MAX_IN_FLIGHT of the library
+DEFAULT_IN_FLIGHT = 4        # frames redraw_sequence keeps in flight (measured, one rank's eighth of a 4K frame on
+                             # one B200: 1.67 / 1.41 / 1.28 / 1.25 / 1.24 ms per frame for 1 / 2 / 3 / 4 / 8)     # 2160 rows / 4 = 540 stripes: per-rank row counts differ by < 1.5 % at 8 ranks
 
 
 # ---- partition arithmetic (mirrors RowMap in csrc/rtb_device.cuh; tested against it) ----------------
@@ -83,7 +83,7 @@ class _DeviceBytes:
 
 
 # control block of the peer exchange, uint32 words; one row of RTB_MAX_PEERS words per frame slot
-_CTL_READY, _CTL_STATUS, _CTL_ACK, _CTL_TIMEOUT, _CTL_WORDS = 0, 64, 128, 192, 256
+_CTL_READY, _CTL_STATUS, _CTL_ACK, _CTL_TIMEOUT, _CTL_WORDS = 0, 128, 256, 384, 512
 _PEER_TIMEOUT_MS = 20000
 
 

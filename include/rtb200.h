@@ -207,7 +207,7 @@ int rtb_render_device(rtb_scene_t scene, const RtbCamera* cam, const RtbRenderOp
 int rtb_finish(rtb_scene_t scene);
 
 /* How many asynchronous wavefront frames (rtb_render_device with stats == NULL) the library keeps in
- * flight: 1 (default) .. 4.  With n > 1, consecutive calls rotate through n private workspaces, and the
+ * flight: 1 (default) .. 8.  With n > 1, consecutive calls rotate through n private workspaces, and the
  * call for frame k+n - not the one for frame k+1 - is what collects frame k.  Issued on different
  * streams, the short per-level kernels of neighbouring frames then run concurrently and fill each
  * other's tails (sequences; a striped multi-GPU frame is a sequence of small frames).  rtb_finish() waits

@@ -184,6 +184,65 @@ def test_unstripe_device_roundtrip(rt, demo):
     assert np.array_equal(frame.cpu().numpy(), full)
 
 
+def test_peer_scatter_assembles_every_ranks_frame(rt, demo):
+    """rtb_peer_* on ONE device: three 'ranks' (all buffers local) render their packed stripes, each
+    scatters them into every rank's framebuffer, sequence numbers and status words arrive in every
+    control block, and rtb_peer_wait / rtb_peer_signal / the timeout path behave.  (Across real GPUs and
+    processes: tools/mgpu_check.py under torchrun.)"""
+    torch = pytest.importorskip("torch")
+    import ctypes as C
+    A = rt._abi
+    lib = A.load()
+    W, H, S, world = 128, 70, 4, 3
+    cam = rt.scenes.demo_camera(W, H)
+    full = demo.redraw(cam)
+    mg = __import__("importlib").import_module("html5-canvas-raytracer_b200.multigpu")
+    frames, ctls = [], []
+    for _ in range(world):
+        for nbytes, lst in ((H * W * 4, frames), (256 * 4, ctls)):
+            p, h = C.c_void_p(), (C.c_uint8 * 64)()
+            A.check(lib.rtb_peer_alloc(nbytes, C.byref(p), h))
+            assert any(h)                                   # an IPC handle was produced
+            lst.append(p.value)
+    VP = C.c_void_p * world
+    pf, pc = VP(*frames), VP(*ctls)
+    padded = lib.rtb_stripe_padded_rows(H, S, world)
+    local = torch.zeros((world, padded + 1, W, 4), dtype=torch.uint8, device="cuda")
+    local[1, padded, 0, 0] = 7                              # rank 1 reports a non-zero status word
+    torch.cuda.synchronize()
+    READY, STATUS, ACK, TMO = 0, 16, 32, 48
+    try:
+        for r in range(world):
+            o = rt.make_opts(stripe_rows=S, stripe_rank=r, stripe_world=world, out_packed=1)
+            demo.redraw_device(cam, o, local[r].data_ptr())
+            A.check(lib.rtb_peer_scatter(C.c_void_p(local[r].data_ptr()), pf, pc, W, H, S, r, world,
+                                         C.c_void_p(local[r, padded].data_ptr()), READY, STATUS, 5, None))
+        for r in range(world):                              # every rank waits for all three sequence numbers
+            A.check(lib.rtb_peer_wait(C.c_void_p(ctls[r] + 4 * READY), world, 5, 2000, C.c_void_p(ctls[r] + 4 * TMO), None))
+            A.check(lib.rtb_peer_signal(pc, world, r, ACK, 5, None))
+        torch.cuda.synchronize()
+        for r in range(world):
+            fr = torch.as_tensor(mg._DeviceBytes(frames[r], (H, W, 4)), device="cuda").cpu().numpy()
+            assert np.array_equal(fr, full), r
+            ctl = torch.as_tensor(mg._DeviceBytes(ctls[r], (256,), "<i4"), device="cuda").cpu().numpy()
+            assert ctl[READY:READY + world].tolist() == [5, 5, 5]
+            assert ctl[STATUS:STATUS + world].tolist() == [0, 7, 0]
+            assert ctl[ACK:ACK + world].tolist() == [5, 5, 5]
+            assert ctl[TMO] == 0
+        # a sequence number that never arrives: the wait gives up and raises the flag instead of hanging
+        A.check(lib.rtb_peer_wait(C.c_void_p(ctls[0] + 4 * READY), world, 6, 50, C.c_void_p(ctls[0] + 4 * TMO), None))
+        torch.cuda.synchronize()
+        ctl = torch.as_tensor(mg._DeviceBytes(ctls[0], (256,), "<i4"), device="cuda").cpu().numpy()
+        assert ctl[TMO] == 1
+        # argument checks
+        assert lib.rtb_peer_scatter(C.c_void_p(local[0].data_ptr()), pf, pc, W + 1, H, S, 0, world, None, 0, 16, 1, None) == A.RTB_ERR_UNSUPPORTED
+        assert lib.rtb_peer_signal(pc, 17, 0, 0, 1, None) == A.RTB_ERR_INVALID
+        assert lib.rtb_peer_wait(None, 1, 1, 1, None, None) == A.RTB_ERR_INVALID
+    finally:
+        for p in frames + ctls:
+            lib.rtb_peer_free(C.c_void_p(p))
+
+
 def test_star_hash_mode_matches_oracle(rt, oracle, demo):
     cam = rt.scenes.demo_camera(256, 144)
     kw = dict(segs=8, star_mode=rt.RTB_STARS_HASH, star_seed=12345)
