@@ -338,10 +338,17 @@ def main():
         kernels = {"pixel_kernel<float>": cls(st_acc["k"], T)}
         kernel_ms = st_acc["k"] / K
         dom = "pixel_kernel<float>"
+    # DRAM bytes of one launch of the dominant kernel, from the committed ncu --set full capture
+    traffic, traffic_note = None, "no ncu capture for this workload"
+    tp = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic.json")
+    if use_wf and CONFIG == "c3_synth1024_4k" and os.path.exists(tp):
+        tj = json.load(open(tp))
+        traffic = tj["dram_bytes_per_launch"]
+        traffic_note = f"{tj['kernel']}, one launch of {tj['launch_us']} us; {tj['source']}"
     roofline = {
         "bound": "fp32", "achieved": round(achieved_tflops * (1 if world == 1 else 1), 3), "peak": round(peak_tflops * world, 3),
         "unit": "TFLOP/s", "frac": round(achieved_tflops / (peak_tflops * world), 4),
-        "traffic": None,
+        "traffic": traffic, "traffic_note": traffic_note,
         "peak_source": f"{info['sm_count']} SMs x 128 FP32 lanes x 2 x sm_max_mhz {sm_max_mhz:.0f} ({peak_src})",
         "flops": f"{FLOPS_PER_TEST} x T, T = {T} reference intersectSphere evaluations per frame (oracle)",
         "dominant_kernel": dom, "dominant": kernels[dom],
