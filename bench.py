@@ -53,7 +53,7 @@ def measured_peaks():
 class ClockSampler(threading.Thread):
     """SM clock + throttle reasons during the timed region (NVML; nvidia-smi as fallback)."""
 
-    def __init__(self, index=0, period=0.05):
+    def __init__(self, index=0, period=0.01):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
@@ -218,7 +218,7 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident timing ------------------------------------------------------------------
-    fif = args.frames_in_flight or mg.DEFAULT_IN_FLIGHT
+    fif = args.frames_in_flight or mg.default_in_flight(world)
     for _ in range(args.warmup):
         sr.redraw(cam, **opts_kw)
     # the sequence path too (its streams and one workspace per frame in flight are created on first use)

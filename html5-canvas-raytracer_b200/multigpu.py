@@ -24,8 +24,14 @@ from .scene import make_opts
 
 DEFAULT_STRIPE_ROWS = 4
 MAX_IN_FLIGHT = 8            # = RTB_MAX_IN_FLIGHT of the library
-DEFAULT_IN_FLIGHT = 4        # frames redraw_sequence keeps in flight (measured, one rank's eighth of a 4K frame on
-                             # one B200: 1.67 / 1.41 / 1.28 / 1.25 / 1.24 ms per frame for 1 / 2 / 3 / 4 / 8)     # 2160 rows / 4 = 540 stripes: per-rank row counts differ by < 1.5 % at 8 ranks
+DEFAULT_IN_FLIGHT = 4        # frames redraw_sequence keeps in flight on one GPU (measured, one rank's eighth of a 4K
+                             # frame on one B200: 1.67 / 1.41 / 1.28 / 1.25 / 1.24 ms per frame for 1 / 2 / 3 / 4 / 8)
+DEFAULT_IN_FLIGHT_MULTI = 8  # ... with world > 1: the exchange adds latency to hide and a rank's share of a frame is
+                             # small (8 GPUs, 4K: 1.383 ms per frame with 4 in flight, 1.351 with 8)
+
+
+def default_in_flight(world: int) -> int:
+    return DEFAULT_IN_FLIGHT if world <= 1 else DEFAULT_IN_FLIGHT_MULTI     # 2160 rows / 4 = 540 stripes: per-rank row counts differ by < 1.5 % at 8 ranks
 
 
 # ---- partition arithmetic (mirrors RowMap in csrc/rtb_device.cuh; tested against it) ----------------
@@ -324,8 +330,8 @@ class StripedRenderer:
                 return self.frame
 
     # -- a sequence of frames (throughput mode) ----------------------------------------------------------
-    def redraw_sequence(self, cameras, on_frame=None, frames_in_flight: int = DEFAULT_IN_FLIGHT, **kw):
-        """Software-pipelined: up to `frames_in_flight` (1..4) frames are enqueued before the host waits
+    def redraw_sequence(self, cameras, on_frame=None, frames_in_flight: int = 0, **kw):
+        """Software-pipelined: up to `frames_in_flight` (1..8; 0 = default_in_flight(world)) frames are enqueued before the host waits
         for the oldest one, each on its own stream with its own library workspace.  Later frames render
         while frame i is in the collective, and the kernels of the frames interleave on the GPU: the
         short per-level launches of one fill the tails of the others.  `on_frame(i, frame)` is called
@@ -334,7 +340,7 @@ class StripedRenderer:
         rank reads the same gathered status words, so every rank repeats the same frames)."""
         import torch
 
-        depth = max(1, min(MAX_IN_FLIGHT, int(frames_in_flight)))
+        depth = max(1, min(MAX_IN_FLIGHT, int(frames_in_flight) or default_in_flight(self.world)))
         n = len(cameras)
         main = torch.cuda.current_stream()
         if self._streams is None:
