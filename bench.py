@@ -8,12 +8,14 @@
              CPU oracle for this exact scene/resolution (tests/golden/counters_*.json); the GPU is
              credited with the oracle's count, never its own.
   value    : whole-job Mrays/s with the scene resident in HBM and the framebuffer left on the device.
-  e2e      : same metric through the host API: the scene description is handed over from host memory
-             every step (rtb_scene_create: H2D) and the frame comes back into a pinned host buffer
-             (rtb_render: D2H) inside the timed region.
+  e2e      : same metric through the host API, host buffers on both sides, all copies inside the timed
+             region: the scene description handed over from host memory (rtb_scene_create: H2D), a sequence
+             of frames rendered by ONE rtb_render_batch call (N > 1: redraw_sequence), every frame copied
+             into pinned host memory (D2H).  e2e.single_frame = the same for one frame per call.
   roofline : FP32 CUDA-core compute (not HBM, not tensor): algorithmic flops = 15 x T, T = the
              reference's intersectSphere evaluations for the frame (oracle counter).
-  N > 1    : torchrun, one rank per GPU; interleaved 16-row stripes; one NCCL all-gather per frame.
+  N > 1    : torchrun, one rank per GPU; interleaved 4-row stripes; exchange by the library's scatter
+             kernel over NVLink peer memory (--exchange nccl: one NCCL all-gather per frame).
              Fixed total work => "scaling": "strong".
 
 `--impl reference` times the CPU float64 restatement of main.js (oracle/, all host threads) on a
@@ -289,6 +291,8 @@ def main():
         finally:
             lib.rtb_scene_destroy(h)
 
+    # (1) one frame at a time: create -> render -> frame on the host -> destroy; the latency a caller of a
+    #     single redraw() sees
     e2e_step()
     barrier()
     k2 = max(3, min(args.steps, 10))
@@ -296,11 +300,51 @@ def main():
     for _ in range(k2):
         e2e_step()
     barrier()
-    e2e_ms = (time.perf_counter() - t0) * 1000 / k2
-    te = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+    single_ms = (time.perf_counter() - t0) * 1000 / k2
+
+    # (2) a frame SEQUENCE through the host API, everything inside the timed region: the scene description
+    #     handed over from host memory (rtb_scene_create: H2D), kb frames rendered with several in flight,
+    #     every frame copied into pinned host memory (D2H under the kernels of the next frames), destroy.
+    #     N = 1: ONE C-ABI call, rtb_render_batch.  N > 1: StripedRenderer.redraw_sequence, rank 0 reads back.
+    kb = max(4, min(args.steps, 16))
+    host_seq = torch.empty((kb, H, W, 4), dtype=torch.uint8).pin_memory() if rank == 0 else None
+    cams_c = (A.RtbCamera * kb)(*([cam_c] * kb))
+    frame_launches = st_acc["launches"] // (2 * max(args.steps, 1))       # own launches per frame (measured above)
+
+    def e2e_sequence():
+        nonlocal e2e_launches
+        h = C.c_void_p()
+        A.check(lib.rtb_scene_create(C.byref(desc.c), C.byref(h)))
+        try:
+            if world <= 1:
+                A.check(lib.rtb_render_batch(h, cams_c, kb, C.byref(e2e_opts), host_seq.data_ptr(), None))
+            else:
+                old = sr.r._h
+                sr.r._h = h
+                try:
+                    def to_host(j, frame):
+                        if rank == 0:
+                            host_seq[j].copy_(frame, non_blocking=True)    # on the frame's own stream
+                    sr.redraw_sequence([cam] * kb, on_frame=to_host, frames_in_flight=fif, **opts_kw)
+                finally:
+                    sr.r._h = old
+                torch.cuda.synchronize()
+            e2e_launches += frame_launches * kb
+        finally:
+            lib.rtb_scene_destroy(h)
+
+    e2e_sequence()
+    barrier()
+    reps = 2
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        e2e_sequence()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1000 / (reps * kb)
+    te = torch.tensor([e2e_ms, single_ms], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_ms = float(te.item())
+    e2e_ms, single_ms = float(te[0].item()), float(te[1].item())
     e2e_value = rays_per_frame / (e2e_ms * 1e-3) / 1e6
 
     sr.close()                               # collective: unmap the peers' buffers, free this rank's
@@ -377,9 +421,17 @@ def main():
         "roofline": roofline,
         "e2e": {"value": round(e2e_value, 2), "unit": "Mrays/s", "ms_per_step": round(e2e_ms, 4),
                 "frames_per_s": round(1000.0 / e2e_ms, 3),
-                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": W * H * 4,
-                "what": "per step: rtb_scene_create (whole scene description from host memory) + rtb_render into a "
-                        "pinned host buffer + rtb_scene_destroy"},
+                "h2d_bytes_per_step": int(round(h2d_bytes / kb)), "d2h_bytes_per_step": W * H * 4,
+                "frames_per_call": kb,
+                "what": f"a sequence of {kb} frames through the host API, all inside the timed region: rtb_scene_create "
+                        "(the whole scene description from host memory, H2D once per sequence: "
+                        f"{h2d_bytes} B) + " +
+                        ("ONE rtb_render_batch call" if world == 1 else "StripedRenderer.redraw_sequence") +
+                        " (every frame D2H into pinned host memory, under the kernels of the next frames) + "
+                        "rtb_scene_destroy",
+                "single_frame": {"ms": round(single_ms, 4), "value": round(rays_per_frame / (single_ms * 1e-3) / 1e6, 2),
+                                 "what": "one frame per call: rtb_scene_create + rtb_render into a pinned host buffer "
+                                         "+ rtb_scene_destroy (nothing overlaps)"}},
         "gpu_launches": int(st_acc["launches"] + e2e_launches),
         "clocks": clocks,
         "device": info,

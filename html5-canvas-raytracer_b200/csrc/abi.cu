@@ -12,6 +12,7 @@
 
 RtbGlobal g_rtb;
 static const int RTB_AUTO_PIXEL_MAX_SPHERES = 32;
+static const int RTB_BATCH_IN_FLIGHT = 4;     // frames rtb_render_batch keeps in flight
 static thread_local char t_err[512] = "";
 // One render / scene operation at a time per process: the workspace, staging buffers and streams are
 // shared library state (the reference's caller is the single JS thread; this keeps other hosts safe).
@@ -388,7 +389,7 @@ int rtb_init(int device) {
   RTB_CUDA(cudaEventCreate(&g_rtb.ev1));
   RTB_CUDA(cudaEventCreate(&g_rtb.ev2));
   RTB_CUDA(cudaEventCreate(&g_rtb.ev3));
-  for (int i = 0; i < 2; i++) {
+  for (int i = 0; i < RTB_MAX_IN_FLIGHT; i++) {
     RTB_CUDA(cudaEventCreateWithFlags(&g_rtb.frame_done[i], cudaEventDisableTiming));
     RTB_CUDA(cudaEventCreateWithFlags(&g_rtb.copy_done[i], cudaEventDisableTiming));
   }
@@ -405,9 +406,13 @@ void rtb_shutdown(void) {
   cudaStreamDestroy(g_rtb.copy_stream);
   cudaEventDestroy(g_rtb.ev0); cudaEventDestroy(g_rtb.ev1);
   cudaEventDestroy(g_rtb.ev2); cudaEventDestroy(g_rtb.ev3);
-  for (int i = 0; i < 2; i++) { cudaEventDestroy(g_rtb.frame_done[i]); cudaEventDestroy(g_rtb.copy_done[i]); }
+  for (int i = 0; i < RTB_MAX_IN_FLIGHT; i++) {
+    cudaEventDestroy(g_rtb.frame_done[i]); cudaEventDestroy(g_rtb.copy_done[i]);
+    if (g_rtb.batch_stream[i]) cudaStreamDestroy(g_rtb.batch_stream[i]);
+    cudaFree(g_rtb.d_frame[i]);
+  }
   for (int i = 0; i < g_rtb.n_timers; i++) cudaEventDestroy(g_rtb.timers[i]);
-  cudaFree(g_rtb.d_frame[0]); cudaFree(g_rtb.d_frame[1]); cudaFree(g_rtb.d_counters);
+  cudaFree(g_rtb.d_counters);
   cudaFree(g_rtb.cached_arena);
   cudaFree(g_rtb.d_star);
   cudaFree(g_rtb.d_peer_counter);
@@ -655,41 +660,97 @@ int rtb_render_batch(rtb_scene_t s, const RtbCamera* cams, int32_t nframes, cons
     rtb_set_error("rtb_render_batch renders whole frames (no stripes / row ranges)");
     return RTB_ERR_UNSUPPORTED;
   }
-  size_t off = 0;
-  RTB_CUDA(cudaEventRecord(g_rtb.ev0, g_rtb.stream));
-  // double-buffered: frame f renders on the compute stream while frame f-1 drains on the copy stream
-  for (int f = 0; f < nframes; f++) {
-    int rc = validate_render(s, &cams[f], o, out);
-    if (rc != RTB_OK) return rc;
-    const int slot = f & 1;
-    const size_t bytes = (size_t)cams[f].width * cams[f].height * 4;
-    rc = ensure_frame(slot, bytes);
-    if (rc != RTB_OK) return rc;
-    if (f >= 2) RTB_CUDA(cudaStreamWaitEvent(g_rtb.stream, g_rtb.copy_done[slot], 0));
-    RtbStats one;
-    memset(&one, 0, sizeof one);
-    rc = render_to_device(s, &cams[f], o, g_rtb.d_frame[slot], g_rtb.stream, stats ? &one : nullptr);
-    if (rc != RTB_OK) return rc;
-    if (stats) {
+  int rc = validate_render(s, &cams[0], o, out);
+  if (rc != RTB_OK) return rc;
+  const size_t bytes = (size_t)cams[0].width * cams[0].height * 4;
+  for (int f = 1; f < nframes; f++) {
+    if ((rc = validate_render(s, &cams[f], o, out)) != RTB_OK) return rc;
+    if (cams[f].width != cams[0].width || cams[f].height != cams[0].height) {
+      rtb_set_error("rtb_render_batch: all frames of a batch have the same size");
+      return RTB_ERR_UNSUPPORTED;
+    }
+  }
+  if (stats) {
+    // instrumented: one frame at a time on the compute stream (per-class event times), the D2H of frame
+    // f-1 on the copy stream under the render of frame f
+    RTB_CUDA(cudaEventRecord(g_rtb.ev0, g_rtb.stream));
+    for (int f = 0; f < nframes; f++) {
+      const int slot = f & 1;
+      if ((rc = ensure_frame(slot, bytes)) != RTB_OK) return rc;
+      if (f >= 2) RTB_CUDA(cudaStreamWaitEvent(g_rtb.stream, g_rtb.copy_done[slot], 0));
+      RtbStats one;
+      memset(&one, 0, sizeof one);
+      if ((rc = render_to_device(s, &cams[f], o, g_rtb.d_frame[slot], g_rtb.stream, &one)) != RTB_OK) return rc;
       stats->nodes += one.nodes; stats->shadow_rays += one.shadow_rays; stats->sphere_tests += one.sphere_tests;
       stats->launches += one.launches; stats->bands += one.bands;
       stats->ms_trace_primary += one.ms_trace_primary; stats->ms_trace_secondary += one.ms_trace_secondary;
       stats->ms_shadow += one.ms_shadow; stats->ms_compose += one.ms_compose;
+      RTB_CUDA(cudaEventRecord(g_rtb.frame_done[slot], g_rtb.stream));
+      RTB_CUDA(cudaStreamWaitEvent(g_rtb.copy_stream, g_rtb.frame_done[slot], 0));
+      RTB_CUDA(cudaMemcpyAsync(out + (size_t)f * bytes, g_rtb.d_frame[slot], bytes, cudaMemcpyDeviceToHost, g_rtb.copy_stream));
+      RTB_CUDA(cudaEventRecord(g_rtb.copy_done[slot], g_rtb.copy_stream));
     }
-    RTB_CUDA(cudaEventRecord(g_rtb.frame_done[slot], g_rtb.stream));
-    RTB_CUDA(cudaStreamWaitEvent(g_rtb.copy_stream, g_rtb.frame_done[slot], 0));
-    RTB_CUDA(cudaMemcpyAsync(out + off, g_rtb.d_frame[slot], bytes, cudaMemcpyDeviceToHost, g_rtb.copy_stream));
-    RTB_CUDA(cudaEventRecord(g_rtb.copy_done[slot], g_rtb.copy_stream));
-    off += bytes;
-  }
-  RTB_CUDA(cudaEventRecord(g_rtb.ev1, g_rtb.stream));
-  RTB_CUDA(cudaStreamSynchronize(g_rtb.copy_stream));
-  RTB_CUDA(cudaStreamSynchronize(g_rtb.stream));
-  if (stats) {
+    RTB_CUDA(cudaEventRecord(g_rtb.ev1, g_rtb.stream));
+    RTB_CUDA(cudaStreamSynchronize(g_rtb.copy_stream));
+    RTB_CUDA(cudaStreamSynchronize(g_rtb.stream));
     float ms = 0;
     RTB_CUDA(cudaEventElapsedTime(&ms, g_rtb.ev0, g_rtb.ev1));
     stats->kernel_ms = ms;
+    return RTB_OK;
   }
+
+  // Throughput path: D frames in flight, each on its own stream with its own workspace and staging
+  // framebuffer; the D2H of a finished frame runs on the copy stream under the kernels of the next ones.
+  // The queue-overflow verdict of frame f is collected just before its workspace is reused (frame f + D);
+  // an overflow (the library has shrunk that frame's bands) restarts the batch at that frame.
+  const int D = std::min(nframes, RTB_BATCH_IN_FLIGHT);
+  const int saved_in_flight = g_rtb.frames_in_flight;
+  if ((rc = rtb_finish_pending(-1)) != RTB_OK) return rc;
+  g_rtb.frames_in_flight = D;
+  g_rtb.next_slot = 0;
+  struct Restore {
+    int v;
+    ~Restore() { (void)rtb_finish_pending(-1); g_rtb.frames_in_flight = v; g_rtb.next_slot = 0; }
+  } restore{saved_in_flight};
+  for (int i = 0; i < D; i++) {
+    if (!g_rtb.batch_stream[i]) RTB_CUDA(cudaStreamCreateWithFlags(&g_rtb.batch_stream[i], cudaStreamNonBlocking));
+    if ((rc = ensure_frame(i, bytes)) != RTB_OK) return rc;
+  }
+  struct InFlight { int frame, lib_slot; };
+  std::vector<InFlight> q;                                // oldest first
+  std::vector<char> buffer_used(D, 0);
+  int f = 0, restarts = 0;
+  while (f < nframes || !q.empty()) {
+    if (f < nframes && (int)q.size() < D) {
+      const int b = f % D;                                // staging framebuffer + stream of this frame
+      cudaStream_t st = g_rtb.batch_stream[b];
+      if (buffer_used[b]) RTB_CUDA(cudaStreamWaitEvent(st, g_rtb.copy_done[b], 0));   // its last D2H has drained
+      const int lib_slot = g_rtb.next_slot % g_rtb.frames_in_flight;
+      if ((rc = render_to_device(s, &cams[f], o, g_rtb.d_frame[b], st, nullptr, /*async=*/true)) != RTB_OK) return rc;
+      RTB_CUDA(cudaEventRecord(g_rtb.frame_done[b], st));
+      RTB_CUDA(cudaStreamWaitEvent(g_rtb.copy_stream, g_rtb.frame_done[b], 0));
+      RTB_CUDA(cudaMemcpyAsync(out + (size_t)f * bytes, g_rtb.d_frame[b], bytes, cudaMemcpyDeviceToHost, g_rtb.copy_stream));
+      RTB_CUDA(cudaEventRecord(g_rtb.copy_done[b], g_rtb.copy_stream));
+      buffer_used[b] = 1;
+      q.push_back({f, lib_slot});
+      f++;
+      continue;
+    }
+    const InFlight h = q.front();
+    q.erase(q.begin());
+    if ((rc = rtb_finish_pending(h.lib_slot)) != RTB_OK) return rc;
+    if (s->deferred_status != RTB_OK) {                   // frame h.frame is invalid: redo it and what followed
+      if ((rc = rtb_finish_pending(-1)) != RTB_OK) return rc;
+      s->deferred_status = RTB_OK;
+      if (++restarts > 64) {
+        rtb_set_error("frame %d of the batch keeps overflowing its ray queues", h.frame);
+        return RTB_ERR_OVERFLOW;
+      }
+      q.clear();
+      f = h.frame;
+    }
+  }
+  RTB_CUDA(cudaStreamSynchronize(g_rtb.copy_stream));
   return RTB_OK;
 }
 

@@ -103,11 +103,12 @@ struct RtbGlobal {
   char name[128] = {0};
   cudaStream_t stream = nullptr, copy_stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
-  cudaEvent_t frame_done[2] = {nullptr, nullptr}, copy_done[2] = {nullptr, nullptr};
+  cudaEvent_t frame_done[RTB_MAX_IN_FLIGHT] = {}, copy_done[RTB_MAX_IN_FLIGHT] = {};
+  cudaStream_t batch_stream[RTB_MAX_IN_FLIGHT] = {};   // rtb_render_batch: one per frame in flight (created on first use)
   // library-owned output staging + wavefront workspace, shared by all scenes (one render in flight
   // per process: the entry points serialise on a mutex), so creating a scene stays cheap
-  uint8_t* d_frame[2] = {nullptr, nullptr};
-  size_t frame_cap[2] = {0, 0};
+  uint8_t* d_frame[RTB_MAX_IN_FLIGHT] = {};
+  size_t frame_cap[RTB_MAX_IN_FLIGHT] = {};
   WfSlot slot[RTB_MAX_IN_FLIGHT];
   int frames_in_flight = 1;                   // 1 .. RTB_MAX_IN_FLIGHT (rtb_set_frames_in_flight)
   int next_slot = 0, last_slot = 0;

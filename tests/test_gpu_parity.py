@@ -166,6 +166,26 @@ def test_batch_equals_single_frames(rt, demo):
         assert np.array_equal(batch[f], demo.redraw(c, segs=8))
 
 
+def test_batch_keeps_frames_in_flight_and_survives_overflow(rt):
+    """rtb_render_batch (wavefront path): four frames in flight, D2H under the next frames; with queues
+    forced tiny it restarts at the overflowing frame and still returns every frame of the batch exactly."""
+    objs = rt.scenes.synth_objects(1024, 1024)
+    cams = rt.scenes.orbit_cameras(160, 90, 9)
+    with rt.Renderer(objs) as r0:
+        refs = [r0.redraw(c, segs=6, kernel=rt.RTB_KERNEL_WAVEFRONT) for c in cams]
+        got = r0.redraw_batch(cams, segs=6, kernel=rt.RTB_KERNEL_WAVEFRONT)
+        assert all(np.array_equal(got[i], refs[i]) for i in range(9))
+        got, st = r0.redraw_batch(cams, stats=True, segs=6, kernel=rt.RTB_KERNEL_WAVEFRONT)   # instrumented path
+        assert all(np.array_equal(got[i], refs[i]) for i in range(9)) and st.nodes > 0
+    os.environ["RTB_WF_CAP_NODES"] = str(160 * 24)
+    try:
+        with rt.Renderer(objs) as r:
+            got = r.redraw_batch(cams, segs=6, kernel=rt.RTB_KERNEL_WAVEFRONT)
+            assert all(np.array_equal(got[i], refs[i]) for i in range(9))
+    finally:
+        del os.environ["RTB_WF_CAP_NODES"]
+
+
 def test_unstripe_device_roundtrip(rt, demo):
     torch = pytest.importorskip("torch")
     cam = rt.scenes.demo_camera(128, 70)
