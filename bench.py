@@ -306,7 +306,7 @@ def main():
     #     handed over from host memory (rtb_scene_create: H2D), kb frames rendered with several in flight,
     #     every frame copied into pinned host memory (D2H under the kernels of the next frames), destroy.
     #     N = 1: ONE C-ABI call, rtb_render_batch.  N > 1: StripedRenderer.redraw_sequence, rank 0 reads back.
-    kb = max(4, min(args.steps, 16))
+    kb = max(4, min(args.steps, 40))                    # 40 x 33 MB of pinned host memory at 4K
     host_seq = torch.empty((kb, H, W, 4), dtype=torch.uint8).pin_memory() if rank == 0 else None
     cams_c = (A.RtbCamera * kb)(*([cam_c] * kb))
     frame_launches = st_acc["launches"] // (2 * max(args.steps, 1))       # own launches per frame (measured above)
