@@ -14,6 +14,7 @@
 // Memory ordering: remote data stores -> __threadfence_system() -> device atomic (last-block election) ->
 // __threadfence_system() -> remote flag store; the reader polls the flag (volatile), fences, then reads.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <stdint.h>
 #include <string.h>
 #include <algorithm>
@@ -82,6 +83,28 @@ __global__ void peer_wait_kernel(const uint32_t* words, int n, uint32_t value, u
     __nanosleep(200);
   }
   __threadfence_system();
+}
+
+// Stream memory operations of the driver API (cuStreamWaitValue32): the stream itself waits for a word
+// in device memory — no kernel, no SM slot.  A spinning wait kernel is only one warp, but the persistent
+// render kernels own every register of every SM, so it can only run in the place of one of their CTAs;
+// with eight frames in flight up to sixteen such waits would be resident.  Looked up at run time so that
+// the library keeps linking against the runtime API only.
+typedef int (*StreamWaitValue32Fn)(void* stream, unsigned long long addr, uint32_t value, unsigned int flags);
+StreamWaitValue32Fn stream_wait_fn() {
+  static bool looked = false;
+  static StreamWaitValue32Fn fn = nullptr;
+  if (!looked) {
+    looked = true;
+    if (!getenv("RTB_PEER_KERNEL_WAIT")) {
+      void* h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+      if (h) {
+        fn = (StreamWaitValue32Fn)dlsym(h, "cuStreamWaitValue32_v2");
+        if (!fn) fn = (StreamWaitValue32Fn)dlsym(h, "cuStreamWaitValue32");
+      }
+    }
+  }
+  return fn;
 }
 
 int check_peers(int world, int rank) {
@@ -200,6 +223,17 @@ int rtb_peer_wait(const void* d_words_u32, int32_t n, uint32_t value, uint32_t t
   if (!g_rtb.inited) { rtb_set_error("rtb_init() has not been called"); return RTB_ERR_NOT_INIT; }
   if (!d_words_u32 || !d_timeout_flag_u32 || n < 1 || n > 32) { rtb_set_error("bad wait arguments"); return RTB_ERR_INVALID; }
   cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : g_rtb.stream;
+  if (timeout_ms == 0) {
+    if (StreamWaitValue32Fn wait = stream_wait_fn()) {
+      bool ok = true;
+      for (int i = 0; i < n && ok; i++)                       // flags 0 = CU_STREAM_WAIT_VALUE_GEQ (cyclic compare)
+        ok = wait((void*)st, (unsigned long long)(uintptr_t)(static_cast<const uint32_t*>(d_words_u32) + i), value, 0u) == 0;
+      if (ok) return RTB_OK;
+      rtb_set_error("cuStreamWaitValue32 failed");
+      return RTB_ERR_CUDA;
+    }
+    timeout_ms = 20000;                                       // driver without stream memory operations
+  }
   peer_wait_kernel<<<1, 32, 0, st>>>(static_cast<const uint32_t*>(d_words_u32), n, value,
                                      (unsigned long long)timeout_ms * 1000000ull,
                                      static_cast<uint32_t*>(d_timeout_flag_u32));

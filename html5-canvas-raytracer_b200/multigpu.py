@@ -90,7 +90,8 @@ class _DeviceBytes:
 
 # control block of the peer exchange, uint32 words; one row of RTB_MAX_PEERS words per frame slot
 _CTL_READY, _CTL_STATUS, _CTL_ACK, _CTL_TIMEOUT, _CTL_WORDS = 0, 128, 256, 384, 512
-_PEER_TIMEOUT_MS = 20000
+_PEER_TIMEOUT_MS = int(os.environ.get("RTB_PEER_TIMEOUT_MS", "0"))   # 0: the stream waits (cuStreamWaitValue32), no
+                                                                    # kernel; > 0: one-warp wait kernel with that timeout
 
 
 class StripedRenderer:

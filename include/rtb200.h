@@ -243,9 +243,11 @@ int rtb_unstripe_device(const void* d_gathered, void* d_frame, int32_t width, in
  *                    rank's status word to ctl[status_offset + rank] and `seq` to ctl[ready_offset + rank]
  *                    of every peer (release order: a peer that sees seq also sees the rows and the status).
  *                    peer_frames / peer_ctl are HOST arrays of `stripe_world` device pointers, own included.
- *   rtb_peer_wait    enqueue a one-warp kernel that holds the stream until n consecutive uint32 words have
- *                    all reached `value` (signed distance; sequence numbers only grow).  After timeout_ms
- *                    it gives up and sets *d_timeout_flag_u32 = 1 instead of hanging the GPU.
+ *   rtb_peer_wait    hold the stream until n consecutive uint32 words have all reached `value` (signed
+ *                    distance; sequence numbers only grow).  timeout_ms > 0: a one-warp kernel that gives
+ *                    up after timeout_ms and sets *d_timeout_flag_u32 = 1 instead of hanging the GPU.
+ *                    timeout_ms == 0: stream memory operations of the driver (cuStreamWaitValue32) - no
+ *                    kernel, no SM slot, no timeout; falls back to the kernel (20 s) if the driver has none.
  *   rtb_peer_signal  enqueue: ctl[word_offset + rank] = value on every peer (e.g. "I am done reading
  *                    framebuffer k": the credit a producer waits for before overwriting it).
  * Replaces, for the multi-GPU mode, the ncclAllGather + rtb_unstripe_device pair. */

@@ -249,6 +249,9 @@ def test_peer_scatter_assembles_every_ranks_frame(rt, demo):
             assert ctl[STATUS:STATUS + world].tolist() == [0, 7, 0]
             assert ctl[ACK:ACK + world].tolist() == [5, 5, 5]
             assert ctl[TMO] == 0
+        # timeout 0 = the stream itself waits (cuStreamWaitValue32), no kernel: already satisfied here
+        A.check(lib.rtb_peer_wait(C.c_void_p(ctls[2] + 4 * READY), world, 5, 0, C.c_void_p(ctls[2] + 4 * TMO), None))
+        torch.cuda.synchronize()
         # a sequence number that never arrives: the wait gives up and raises the flag instead of hanging
         A.check(lib.rtb_peer_wait(C.c_void_p(ctls[0] + 4 * READY), world, 6, 50, C.c_void_p(ctls[0] + 4 * TMO), None))
         torch.cuda.synchronize()
