@@ -398,15 +398,24 @@ class FrameBatchRenderer:
         self.mine = torch.zeros((height, width, 4), dtype=torch.uint8, device=dev)
         self.step = torch.empty((max(world, 1), height, width, 4), dtype=torch.uint8, device=dev)
 
-    def redraw_step(self, cameras: Sequence, first: int, stats=None, **kw):
-        """Frames first .. first+world-1 (cameras beyond the end are skipped).  Returns [world,H,W,4]."""
+    def redraw_step(self, cameras: Sequence, first: int, stats=None, objects_for_frame=None, **kw):
+        """Frames first .. first+world-1 (cameras beyond the end are skipped).  Returns [world,H,W,4].
+        objects_for_frame(f) -> the frame's own (re-sorted) object list: config C5 re-sorts the scene
+        for every camera position (scenes.orbit_frames); without it every frame uses self.r's scene."""
         import torch
         import torch.distributed as dist
+
+        from .render import Renderer
 
         stream = torch.cuda.current_stream().cuda_stream
         f = first + self.rank
         if f < len(cameras):
-            self.r.redraw_device(cameras[f], make_opts(**kw), self.mine.data_ptr(), stream, stats)
+            if objects_for_frame is not None:
+                with Renderer(objects_for_frame(f), device=torch.cuda.current_device()) as r:
+                    r.redraw_device(cameras[f], make_opts(**kw), self.mine.data_ptr(), stream, stats)
+                    torch.cuda.current_stream().synchronize()
+            else:
+                self.r.redraw_device(cameras[f], make_opts(**kw), self.mine.data_ptr(), stream, stats)
         if self.world <= 1:
             self.step[0].copy_(self.mine)
         else:

@@ -112,6 +112,16 @@ def orbit_cameras(width: int, height: int, nframes: int = 360) -> List[Camera]:
     return cams
 
 
+def orbit_frames(width: int, height: int, nframes: int = 360, textures=None):
+    """Config C5 with the host-side scene preparation the reference would do for each frame: the
+    objects re-sorted with main.js's comparator (159-163) for THAT frame's camera origin — array order
+    decides closest-hit ties, the self-shadow index and the occluder order.  Yields (objects, camera)."""
+    if textures is None:
+        textures = load_planet_textures()
+    for cam in orbit_cameras(width, height, nframes):
+        yield demo_objects(origin=tuple(cam.origin), textures=textures), cam
+
+
 def config_workload(name: str) -> Tuple[str, int, int, int, int]:
     """(scene, width, height, segs, spp_grid) of the named BASELINE.json config."""
     table = {

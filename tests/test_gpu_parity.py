@@ -186,6 +186,29 @@ def test_batch_keeps_frames_in_flight_and_survives_overflow(rt):
         del os.environ["RTB_WF_CAP_NODES"]
 
 
+def test_c5_orbit_frames_with_per_frame_sort(rt, oracle):
+    """Config C5: each orbit frame rendered from its own re-sorted scene (scenes.orbit_frames), basis
+    camera; the fp64 kernel stays bit-exact against the oracle, FrameBatchRenderer takes the per-frame
+    scenes."""
+    torch = pytest.importorskip("torch")
+    mg = __import__("importlib").import_module("html5-canvas-raytracer_b200.multigpu")
+    frames = list(rt.scenes.orbit_frames(96, 54, nframes=6))[:4]
+    refs = []
+    for objs, cam in frames:
+        ref, cnt = oracle.render(rt.SceneDesc(objs), cam, rt.make_opts(segs=6))
+        with rt.Renderer(objs) as r:
+            img, st = r.redraw(cam, stats=True, segs=6, precision=rt.RTB_PRECISION_FP64)
+        assert np.array_equal(img, ref) and st.nodes == cnt["nodes"]
+        refs.append(ref)
+    with rt.Renderer(frames[0][0]) as r0:
+        fb = mg.FrameBatchRenderer(r0, 96, 54, 0, 1)
+        for f in range(4):
+            out = fb.redraw_step([c for _, c in frames], f, objects_for_frame=lambda i: frames[i][0],
+                                 segs=6, precision=rt.RTB_PRECISION_FP64)
+            torch.cuda.synchronize()
+            assert np.array_equal(out[0].cpu().numpy(), refs[f])
+
+
 def test_unstripe_device_roundtrip(rt, demo):
     torch = pytest.importorskip("torch")
     cam = rt.scenes.demo_camera(128, 70)
