@@ -207,7 +207,7 @@ def main():
     cam = rt.scenes.demo_camera(W, H)
     renderer = rt.Renderer(objs, device=local_rank)
     sr = mg.StripedRenderer(renderer, W, H, rank, world, exchange=args.exchange)
-    xl = 0 if world <= 1 else (2 if sr.exchange == "p2p" else 1)    # own exchange kernels per frame (scatter + signal | unstripe)
+    xl = 0 if world <= 1 else (4 if sr.exchange == "p2p" else 1)    # own exchange kernels per frame (signal, 2 waits, scatter | unstripe)
     A = rt._abi
     # the product's own choice (RTB_KERNEL_AUTO): wavefront for the 1024-sphere scene, fused per-pixel
     # kernel for the 14-sphere demo configs

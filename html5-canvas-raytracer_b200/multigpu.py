@@ -90,8 +90,9 @@ class _DeviceBytes:
 
 # control block of the peer exchange, uint32 words; one row of RTB_MAX_PEERS words per frame slot
 _CTL_READY, _CTL_STATUS, _CTL_ACK, _CTL_TIMEOUT, _CTL_WORDS = 0, 128, 256, 384, 512
-_PEER_TIMEOUT_MS = int(os.environ.get("RTB_PEER_TIMEOUT_MS", "0"))   # 0: the stream waits (cuStreamWaitValue32), no
-                                                                    # kernel; > 0: one-warp wait kernel with that timeout
+# > 0: one-warp wait kernel that gives up after that many ms (a dead peer becomes an error, not a hang);
+# 0: the stream itself waits (cuStreamWaitValue32: no kernel, no SM slot, no timeout).  Same speed at 8 GPUs.
+_PEER_TIMEOUT_MS = int(os.environ.get("RTB_PEER_TIMEOUT_MS", "20000"))
 
 
 class StripedRenderer:
