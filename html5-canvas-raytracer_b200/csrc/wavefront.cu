@@ -337,17 +337,17 @@ __device__ __noinline__ void process_hit(const WfParams& P, const WfRay& r, unsi
       const DevMaterial<float>& m = P.sc.mtl[hit_i];
       p[0] = o[0] + d[0] * best; p[1] = o[1] + d[1] * best; p[2] = o[2] + d[2] * best;
       float nn[3] = {p[0] - g.x, p[1] - g.y, p[2] - g.z};
-      const float nl = sqrtf(nn[0] * nn[0] + nn[1] * nn[1] + nn[2] * nn[2]);
-      if (nl != 0.f) { const float q = 1.f / nl; nn[0] *= q; nn[1] *= q; nn[2] *= q; }
+      const float nl = nn[0] * nn[0] + nn[1] * nn[1] + nn[2] * nn[2];
+      if (nl != 0.f) { const float q = rsqrtf(nl); nn[0] *= q; nn[1] *= q; nn[2] *= q; }
       const float l[3] = {flip ? -nn[0] : nn[0], flip ? -nn[1] : nn[1], flip ? -nn[2] : nn[2]};
       const float a1 = m.albedo[1], a2 = m.albedo[2], a3 = m.albedo[3], a4 = m.albedo[4];
       const float dn = d[0] * nn[0] + d[1] * nn[1] + d[2] * nn[2];
       if (a3 > 0.f) {                                     // main.js:233-239
         const float tt = -(2.f * dn);
         rdir[0] = d[0] + nn[0] * tt; rdir[1] = d[1] + nn[1] * tt; rdir[2] = d[2] + nn[2] * tt;
-        const float len = sqrtf(rdir[0] * rdir[0] + rdir[1] * rdir[1] + rdir[2] * rdir[2]);
+        const float len = rdir[0] * rdir[0] + rdir[1] * rdir[1] + rdir[2] * rdir[2];
         if (len != 0.f) {
-          const float q = 1.f / len; rdir[0] *= q; rdir[1] *= q; rdir[2] *= q;
+          const float q = rsqrtf(len); rdir[0] *= q; rdir[1] *= q; rdir[2] *= q;
           want_refl = r.segs_left > 1;                    // a child with segs == 0 returns [0,0,0]
           w_refl = a3;
         }
@@ -365,9 +365,9 @@ __device__ __noinline__ void process_hit(const WfParams& P, const WfRay& r, unsi
           const float tt = -(2.f * (d[0] * norm[0] + d[1] * norm[1] + d[2] * norm[2]));
           fdir[0] = d[0] + norm[0] * tt; fdir[1] = d[1] + norm[1] * tt; fdir[2] = d[2] + norm[2] * tt;
         }
-        const float len = sqrtf(fdir[0] * fdir[0] + fdir[1] * fdir[1] + fdir[2] * fdir[2]);
+        const float len = fdir[0] * fdir[0] + fdir[1] * fdir[1] + fdir[2] * fdir[2];
         if (len != 0.f) {
-          const float q = 1.f / len; fdir[0] *= q; fdir[1] *= q; fdir[2] *= q;
+          const float q = rsqrtf(len); fdir[0] *= q; fdir[1] *= q; fdir[2] *= q;
           want_refr = r.segs_left > 1;
           w_refr = a4;
         }
@@ -375,8 +375,8 @@ __device__ __noinline__ void process_hit(const WfParams& P, const WfRay& r, unsi
       // sampler (main.js:320); u,v only matter to the texture sampler
       float u = 0.f, v = 0.f, rgb[3];
       if (m.sampler_kind == RTB_SAMPLER_TEXTURE) {
-        u = atan2f(-nn[2], -nn[0]) / 3.14159265358979323846f / 2.f + 0.5f;
-        v = asinf(-nn[1]) / (3.14159265358979323846f / 2.f) / 2.f + 0.5f;
+        u = atan2f(-nn[2], -nn[0]) * 0.15915494309189535f + 0.5f;     // / pi / 2
+        v = asinf(-nn[1]) * 0.31830988618379069f + 0.5f;              // / (pi / 2) / 2
       }
       uint32_t px = 0, py = 0, sub = 0;
       if (m.sampler_kind == RTB_SAMPLER_STARS && P.fr64.star_mode == RTB_STARS_HASH) {
@@ -393,20 +393,20 @@ __device__ __noinline__ void process_hit(const WfParams& P, const WfRay& r, unsi
         for (int k = 0; k < P.sc.n_lights; k++) {
           float sv[3] = {P.sc.lights[k][0] - p[0], P.sc.lights[k][1] - p[1], P.sc.lights[k][2] - p[2]};
           const float mag = sv[0] * sv[0] + sv[1] * sv[1] + sv[2] * sv[2];
-          const float len = sqrtf(mag);
-          if (len != 0.f) { const float qq = 1.f / len; sv[0] *= qq; sv[1] *= qq; sv[2] *= qq; }
+          float inv_mag = 0.f;
+          if (mag != 0.f) { const float qq = rsqrtf(mag); sv[0] *= qq; sv[1] *= qq; sv[2] *= qq; inv_mag = qq * qq; }
           const float sdot = sv[0] * l[0] + sv[1] * l[1] + sv[2] * l[2];
           if (!(sdot > 0.f)) continue;
           mask |= 1u << k;
-          q[k] = sdot / mag;
+          q[k] = (mag != 0.f) ? sdot * inv_mag : sdot / mag;
           if (a2 > 0.f) {
             // light_ref = normal3D(reflect3D(-sv, l)); spec_dot = dir . (-light_ref)
             const float tt = 2.f * sdot;                   // -(2 * dot(-sv, l))
             float lr[3] = {-sv[0] + l[0] * tt, -sv[1] + l[1] * tt, -sv[2] + l[2] * tt};
-            const float ll = sqrtf(lr[0] * lr[0] + lr[1] * lr[1] + lr[2] * lr[2]);
-            if (ll != 0.f) { const float qq = 1.f / ll; lr[0] *= qq; lr[1] *= qq; lr[2] *= qq; }
+            const float ll = lr[0] * lr[0] + lr[1] * lr[1] + lr[2] * lr[2];
+            if (ll != 0.f) { const float qq = rsqrtf(ll); lr[0] *= qq; lr[1] *= qq; lr[2] *= qq; }
             const float sd = -(d[0] * lr[0] + d[1] * lr[1] + d[2] * lr[2]);
-            if (sd > 0.f) sp[k] = powf(sd, m.specular_exponent);
+            if (sd > 0.f) sp[k] = __powf(sd, m.specular_exponent);
           }
         }
       }
