@@ -412,13 +412,14 @@ __device__ __noinline__ void process_hit(const WfParams& P, const WfRay& r, unsi
       }
       if (mask) first_light = __ffs((int)mask) - 1;
       P.b.pos[node] = make_float4(p[0], p[1], p[2], __int_as_float(hit_i));
-      P.b.base[node] = make_float4(rgb[0], rgb[1], rgb[2], __int_as_float((int)mask));
+      // base.w: facing-light mask (bits 0-7) + which child slots will be filled (bits 8, 9) — the compose
+      // pass reads a child colour only when its bit is set, so the slots need no zero-initialisation
+      P.b.base[node] = make_float4(rgb[0], rgb[1], rgb[2],
+                                   __int_as_float((int)(mask | (want_refl ? 0x100u : 0u) | (want_refr ? 0x200u : 0u))));
       P.b.lq[node] = make_float4(q[0], sp[0], q[1], sp[1]);
       if (P.b.lq2) P.b.lq2[node] = make_float4(q[2], sp[2], q[3], sp[3]);
       P.b.acc[node] = make_float4(P.sc.light_intensity, 0.f, 0.f, 0.f);
     }
-    P.b.child_a[node] = make_float4(0.f, 0.f, 0.f, 0.f);
-    P.b.child_b[node] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 
   // ---- warp-compacted child allocation (north star: ballot/shuffle compaction of live rays) ---------
@@ -707,7 +708,7 @@ RTB_DEVINL void shadow_chunks(const WfParams& P, int k, const float4* __restrict
       if (active[q]) {
         float4 a = P.b.acc[node[q]];
         a.x = I[q];
-        const uint32_t lmask = (uint32_t)__float_as_int(P.b.base[node[q]].w);
+        const uint32_t lmask = (uint32_t)__float_as_int(P.b.base[node[q]].w) & 0xffu;
         if (I[q] != 0.f) {                                 // main.js:305-313
           const float4 lq = (k < 2) ? P.b.lq[node[q]] : P.b.lq2[node[q]];
           const float qk = (k & 1) ? lq.z : lq.x, sk = (k & 1) ? lq.w : lq.y;
@@ -778,7 +779,9 @@ RTB_DEVINL void node_colour(const WfParams& P, uint32_t node, float col[3]) {
   if (hit_i < 0) { col[0] = bs.x; col[1] = bs.y; col[2] = bs.z; return; }
   const DevMaterial<float>& m = P.sc.mtl[hit_i];
   const float4 a = P.b.acc[node];
-  const float4 ca = P.b.child_a[node], cb = P.b.child_b[node];
+  const uint32_t bits = (uint32_t)__float_as_int(bs.w);
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 ca = (bits & 0x100u) ? P.b.child_a[node] : zero, cb = (bits & 0x200u) ? P.b.child_b[node] : zero;
   const float di = js_min<float>(1.f, a.y) * m.albedo[1];
   const float si = js_min<float>(1.f, a.z) * m.albedo[2];
   const float rgb[3] = {bs.x, bs.y, bs.z};
