@@ -416,9 +416,11 @@ __device__ __noinline__ void process_hit(const WfParams& P, const WfRay& r, unsi
       // pass reads a child colour only when its bit is set, so the slots need no zero-initialisation
       P.b.base[node] = make_float4(rgb[0], rgb[1], rgb[2],
                                    __int_as_float((int)(mask | (want_refl ? 0x100u : 0u) | (want_refr ? 0x200u : 0u))));
-      P.b.lq[node] = make_float4(q[0], sp[0], q[1], sp[1]);
-      if (P.b.lq2) P.b.lq2[node] = make_float4(q[2], sp[2], q[3], sp[3]);
-      P.b.acc[node] = make_float4(P.sc.light_intensity, 0.f, 0.f, 0.f);
+      if (mask) {                                         // no facing light: never queued, never accumulated
+        P.b.lq[node] = make_float4(q[0], sp[0], q[1], sp[1]);
+        if (P.b.lq2) P.b.lq2[node] = make_float4(q[2], sp[2], q[3], sp[3]);
+        P.b.acc[node] = make_float4(P.sc.light_intensity, 0.f, 0.f, 0.f);
+      }
     }
   }
 
@@ -778,9 +780,9 @@ RTB_DEVINL void node_colour(const WfParams& P, uint32_t node, float col[3]) {
   const int hit_i = __float_as_int(ps.w);
   if (hit_i < 0) { col[0] = bs.x; col[1] = bs.y; col[2] = bs.z; return; }
   const DevMaterial<float>& m = P.sc.mtl[hit_i];
-  const float4 a = P.b.acc[node];
   const uint32_t bits = (uint32_t)__float_as_int(bs.w);
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 a = (bits & 0xffu) ? P.b.acc[node] : zero;   // diffuse / specular sums exist only for lit nodes
   const float4 ca = (bits & 0x100u) ? P.b.child_a[node] : zero, cb = (bits & 0x200u) ? P.b.child_b[node] : zero;
   const float di = js_min<float>(1.f, a.y) * m.albedo[1];
   const float si = js_min<float>(1.f, a.z) * m.albedo[2];
