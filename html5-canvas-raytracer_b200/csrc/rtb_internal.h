@@ -105,8 +105,8 @@ struct RtbGlobal {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
   cudaEvent_t frame_done[RTB_MAX_IN_FLIGHT] = {}, copy_done[RTB_MAX_IN_FLIGHT] = {};
   cudaStream_t batch_stream[RTB_MAX_IN_FLIGHT] = {};   // rtb_render_batch: one per frame in flight (created on first use)
-  // library-owned output staging + wavefront workspace, shared by all scenes (one render in flight
-  // per process: the entry points serialise on a mutex), so creating a scene stays cheap
+  // library-owned output staging + wavefront workspaces (one per frame in flight), shared by all scenes
+  // (the entry points serialise on a mutex), so creating a scene stays cheap
   uint8_t* d_frame[RTB_MAX_IN_FLIGHT] = {};
   size_t frame_cap[RTB_MAX_IN_FLIGHT] = {};
   WfSlot slot[RTB_MAX_IN_FLIGHT];

@@ -12,8 +12,10 @@
  *             what it needs during the call and keeps no caller pointer.
  * Errors    : 0 = RTB_OK, negative = error; message via rtb_last_error() (thread-local).
  *             The library never aborts and never throws across this boundary.
- * Threading : synchronous; one render in flight per scene handle (the reference's caller is the
- *             single JS thread).  CUDA streams are library-owned.
+ * Threading : entry points serialise on a process-wide mutex (the reference's caller is the single JS
+ *             thread).  rtb_render is synchronous; rtb_render_device only enqueues, and with
+ *             rtb_set_frames_in_flight(n) up to n such frames overlap on the GPU; rtb_render_batch keeps
+ *             several frames in flight internally.  Streams are library-owned unless one is passed in.
  * No CPU fallback: every entry point that computes needs a CUDA device and fails with
  *             RTB_ERR_NO_DEVICE / RTB_ERR_CUDA otherwise.
  *
