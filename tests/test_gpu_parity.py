@@ -227,7 +227,8 @@ def test_unstripe_device_roundtrip(rt, demo):
     assert np.array_equal(frame.cpu().numpy(), full)
 
 
-def test_peer_scatter_assembles_every_ranks_frame(rt, demo):
+@pytest.mark.parametrize("S", [4, 1])
+def test_peer_scatter_assembles_every_ranks_frame(rt, demo, S):
     """rtb_peer_* on ONE device: three 'ranks' (all buffers local) render their packed stripes, each
     scatters them into every rank's framebuffer, sequence numbers and status words arrive in every
     control block, and rtb_peer_wait / rtb_peer_signal / the timeout path behave.  (Across real GPUs and
@@ -236,7 +237,7 @@ def test_peer_scatter_assembles_every_ranks_frame(rt, demo):
     import ctypes as C
     A = rt._abi
     lib = A.load()
-    W, H, S, world = 128, 70, 4, 3
+    W, H, world = 128, 70, 3
     cam = rt.scenes.demo_camera(W, H)
     full = demo.redraw(cam)
     mg = __import__("importlib").import_module("html5-canvas-raytracer_b200.multigpu")

@@ -13,7 +13,7 @@ with rt.Renderer(objs) as r:
     for world in [int(a) for a in sys.argv[1:]] or [1, 2, 4, 8]:
         res = []
         for rank in sorted({0, world // 2, world - 1}):
-            o = rt.make_opts(segs=8, kernel=rt.RTB_KERNEL_WAVEFRONT, stripe_rows=4, stripe_rank=rank,
+            o = rt.make_opts(segs=8, kernel=rt.RTB_KERNEL_WAVEFRONT, stripe_rows=int(os.environ.get("STRIPE_ROWS", "4")), stripe_rank=rank,
                              stripe_world=world, out_packed=1)
             for _ in range(3):
                 r.redraw_device(cam, o, dev.data_ptr())
