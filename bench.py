@@ -14,7 +14,7 @@
              into pinned host memory (D2H).  e2e.single_frame = the same for one frame per call.
   roofline : FP32 CUDA-core compute (not HBM, not tensor): algorithmic flops = 15 x T, T = the
              reference's intersectSphere evaluations for the frame (oracle counter).
-  N > 1    : torchrun, one rank per GPU; interleaved 4-row stripes; exchange by the library's scatter
+  N > 1    : torchrun, one rank per GPU; interleaved single-row stripes; exchange by the library's scatter
              kernel over NVLink peer memory (--exchange nccl: one NCCL all-gather per frame).
              Fixed total work => "scaling": "strong".
 
