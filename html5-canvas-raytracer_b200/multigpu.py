@@ -3,9 +3,10 @@
   * row stripes (BASELINE config 3): stripes of `stripe_rows` rows are dealt round-robin to the ranks
     (stripe i -> rank i % world).  Contiguous bands would be badly imbalanced — the horizon splits the
     demo into cheap sky rows and expensive floor/sphere rows.  Every rank renders its
-    rows PACKED into a [padded_rows, W, 4] buffer, one `all_gather_into_tensor` (NCCL over NVLink)
-    assembles [world, padded_rows, W, 4] on every rank, and a small kernel de-interleaves it into
-    the row-major framebuffer.  The gather is the only collective and exists only when world > 1.
+    rows PACKED into a [padded_rows, W, 4] buffer; the exchange is either the library's scatter kernel
+    over NVLink peer memory (rows stored straight into every rank's framebuffer) or one
+    `all_gather_into_tensor` (NCCL) plus a de-interleave kernel.  It exists only when world > 1.
+    Sequences keep several frames in flight per GPU (redraw_sequence).
   * frame batches (config 5): frame f -> rank f % world; the rendered frames are all-gathered.
 
 torch is used for process-group plumbing and device buffers only; all rendering goes through the
@@ -33,7 +34,7 @@ DEFAULT_IN_FLIGHT_MULTI = 8  # ... with world > 1: the exchange adds latency to 
 
 
 def default_in_flight(world: int) -> int:
-    return DEFAULT_IN_FLIGHT if world <= 1 else DEFAULT_IN_FLIGHT_MULTI     # 2160 rows / 4 = 540 stripes: per-rank row counts differ by < 1.5 % at 8 ranks
+    return DEFAULT_IN_FLIGHT if world <= 1 else DEFAULT_IN_FLIGHT_MULTI
 
 
 # ---- partition arithmetic (mirrors RowMap in csrc/rtb_device.cuh; tested against it) ----------------
