@@ -106,16 +106,37 @@ def build_objects(rt, scene):
     return rt.scenes.demo_objects() if scene == "demo" else rt.scenes.synth_objects(1024, 1024)
 
 
+def host_threads():
+    """Host threads this process may use.  Counted from the affinity mask, not from OMP_NUM_THREADS: torchrun
+    exports OMP_NUM_THREADS=1 to every rank, which would silently turn the CPU arm into a 1-thread run."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def workload_config(scene, W, H, segs, g, cnt):
+    """`config` of the JSON line: the WORKLOAD only, identical for the GPU arm and the CPU reference arm
+    (what each arm runs it with is in `engine`)."""
+    return {"workload": CONFIG,
+            "scene": "synth1024 (numpy default_rng(1024), reference sort)" if scene != "demo" else "demo (main.js:107-163)",
+            "width": W, "height": H, "segs": segs, "spp": g * g, "n_spheres": cnt["n_spheres"],
+            "rays_per_frame": cnt["rays"],
+            "l2": "no flush between frames: a frame's working set (ray/node queues, ~2.7 GB at 4K) exceeds the 126 MB L2"}
+
+
 def cpu_sample(rt, desc, cam, segs, g, threads=0, rows=CPU_SAMPLE_ROWS):
     """Oracle (C port of main.js) on `rows` evenly spaced rows of the frame.  Returns (Mrays/s, dict)."""
     from oracle import oracle
     oracle.build()
+    if threads <= 0:
+        threads = host_threads()
     step = max(1, cam.height // rows)
     t0 = time.perf_counter()
     _, cnt = oracle.render(desc, cam, rt.make_opts(segs=segs, spp_grid=g), row_step=step, threads=threads)
     dt = time.perf_counter() - t0
     nrows = len(range(0, cam.height, step))
-    cores = oracle.max_threads() if threads <= 0 else threads
+    cores = threads
     return cnt["rays"] / dt / 1e6, {
         "seconds": round(dt, 3), "rays": cnt["rays"], "sphere_tests": cnt["sphere_tests"], "cores": cores,
         "sample": f"{nrows} evenly spaced rows (every {step}th) of the {cam.width}x{cam.height} frame, "
@@ -145,9 +166,10 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(1000 * total / args.steps, 3), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": CONFIG, "scene": scene, "width": W, "height": H, "segs": segs,
-                   "note": "CPU float64 restatement of main.js (oracle/rt_oracle.c); the reference is browser "
-                           "JavaScript and this image has no JS engine"},
+        "config": workload_config(scene, W, H, segs, g, load_counters(CONFIG)),
+        "engine": {"what": "CPU float64 restatement of main.js (oracle/rt_oracle.c), OpenMP over rows; the reference "
+                           "is browser JavaScript and this image has no JS engine",
+                   "threads": info["cores"]},
         "cpu_baseline": {"value": round(value, 4), "unit": "Mrays/s", "cores": info["cores"], "kind": "port",
                          "sample": info["sample"]},
         "e2e": {"value": round(value, 4), "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -175,7 +197,9 @@ def main():
     ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"],
                     help="multi-GPU framebuffer exchange: peer-memory scatter kernel or NCCL all-gather")
     ap.add_argument("--frames-in-flight", type=int, default=0,
-                    help="frames the sequence keeps in flight (0 = the host layer's default)")
+                    help="wavefront passes the sequence keeps in flight (0 = the host layer's default)")
+    ap.add_argument("--group", type=int, default=0,
+                    help="frames per wavefront pass in sequence mode (0 = the host layer's default: the GPU count)")
     ap.add_argument("--config", default=CONFIG,
                     choices=["c3_synth1024_4k", "c2_demo_1080p_segs5", "c4_demo_4k_16spp"],
                     help="BASELINE.json config; the default (configs[2]) is the one the metric is quoted on")
@@ -206,8 +230,12 @@ def main():
     objs = build_objects(rt, scene)
     cam = rt.scenes.demo_camera(W, H)
     renderer = rt.Renderer(objs, device=local_rank)
-    sr = mg.StripedRenderer(renderer, W, H, rank, world, exchange=args.exchange)
-    xl = 0 if world <= 1 else (4 if sr.exchange == "p2p" else 1)    # own exchange kernels per frame (signal, 2 waits, scatter | unstripe)
+    fif = args.frames_in_flight or mg.default_in_flight(world)
+    sr = mg.StripedRenderer(renderer, W, H, rank, world, exchange=args.exchange, group=args.group,
+                            slots=max(fif, 3) if world > 1 else 0)
+    G = sr.G                                  # frames per wavefront pass (sequence mode)
+    # own exchange kernels per GROUP (signal, 2 waits, scatter | one unstripe per frame)
+    xl = 0 if world <= 1 else (4 if sr.exchange == "p2p" else G)
     A = rt._abi
     # the product's own choice (RTB_KERNEL_AUTO): wavefront for the 1024-sphere scene, fused per-pixel
     # kernel for the 14-sphere demo configs
@@ -220,19 +248,19 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident timing ------------------------------------------------------------------
-    fif = args.frames_in_flight or mg.default_in_flight(world)
     for _ in range(args.warmup):
         sr.redraw(cam, **opts_kw)
-    # the sequence path too (its streams and one workspace per frame in flight are created on first use)
-    sr.redraw_sequence([cam] * max(args.warmup, fif + 1), frames_in_flight=fif, **opts_kw)
+    # the sequence path too (its streams and one workspace per pass in flight are created on first use)
+    sr.redraw_sequence([cam] * max(args.warmup, (fif + 1) * G), frames_in_flight=fif, **opts_kw)
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
     st_acc = {"p": 0.0, "s": 0.0, "sh": 0.0, "c": 0.0, "k": 0.0, "launches": 0, "nodes": 0, "shadow": 0}
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    # K frames as a sequence: with N > 1 the render of frame i+1 overlaps the all-gather of frame i
-    # (StripedRenderer.redraw_sequence); every frame is fully assembled on every rank inside the region.
+    # K frames as a sequence (StripedRenderer.redraw_sequence): groups of G frames per wavefront pass, `fif`
+    # passes in flight, so the render of one group overlaps the exchange of the previous one; every frame is
+    # fully assembled on every rank inside the region.
     repeats = sr.redraw_sequence([cam] * args.steps, frames_in_flight=fif, **opts_kw)   # no instrumentation inside
     ev1.record()
     barrier()
@@ -246,13 +274,18 @@ def main():
 
     # per-kernel-class durations (CUDA events inside the library, on the launching stream): measured
     # live, right after the timed region, over the same number of frames
-    for _ in range(args.steps):
+    # (one group of G frames per instrumented pass, the launch shape of the timed region; normalised per frame)
+    n_passes = len(mg.split_groups(args.steps, G))
+    pass_launches = 0
+    for _ in range(n_passes):
         st = A.RtbStats()
-        sr.redraw(cam, stats=st, **opts_kw)
+        sr.redraw_group([cam] * G, stats=st, **opts_kw)
         st_acc["p"] += st.ms_trace_primary; st_acc["s"] += st.ms_trace_secondary
         st_acc["sh"] += st.ms_shadow; st_acc["c"] += st.ms_compose; st_acc["k"] += st.kernel_ms
-        st_acc["launches"] += 2 * (st.launches + xl)                           # timed + instrumented pass
-        st_acc["nodes"], st_acc["shadow"] = int(st.nodes), int(st.shadow_rays)
+        pass_launches = st.launches + xl
+        st_acc["launches"] += 2 * pass_launches                                # timed + instrumented pass
+        st_acc["nodes"], st_acc["shadow"] = int(st.nodes) // G, int(st.shadow_rays) // G
+    inst_frames = n_passes * G                                                 # frames the sums above cover
     barrier()
 
     # ---- end to end through the host API (rank-local D2H on rank 0; scene handed over per step) ----
@@ -309,7 +342,6 @@ def main():
     kb = max(4, min(args.steps, 40))                    # 40 x 33 MB of pinned host memory at 4K
     host_seq = torch.empty((kb, H, W, 4), dtype=torch.uint8).pin_memory() if rank == 0 else None
     cams_c = (A.RtbCamera * kb)(*([cam_c] * kb))
-    frame_launches = st_acc["launches"] // (2 * max(args.steps, 1))       # own launches per frame (measured above)
 
     def e2e_sequence():
         nonlocal e2e_launches
@@ -329,7 +361,7 @@ def main():
                 finally:
                     sr.r._h = old
                 torch.cuda.synchronize()
-            e2e_launches += frame_launches * kb
+            e2e_launches += pass_launches * len(mg.split_groups(kb, G))
         finally:
             lib.rtb_scene_destroy(h)
 
@@ -360,7 +392,7 @@ def main():
     sm_max_mhz = float(peaks.get("sm_max_mhz") or 1965.0)
     peak_tflops = info["sm_count"] * 128 * 2 * sm_max_mhz * 1e6 / 1e12
     achieved_tflops = FLOPS_PER_TEST * T / (ms_step * 1e-3) / 1e12
-    K = args.steps
+    K = inst_frames
     n_sub = W * H * g * g
     T_primary = n_sub * cnt["n_spheres"]
     T_secondary = (cnt["nodes"] - n_sub) * cnt["n_spheres"]
@@ -407,17 +439,15 @@ def main():
         "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "frames_per_s": round(1000.0 / ms_step, 3),
-        "config": {"workload": CONFIG,
-                   "scene": "synth1024 (numpy default_rng(1024), reference sort)" if scene != "demo" else "demo (main.js:107-163)",
-                   "width": W, "height": H, "segs": segs, "spp": g * g, "n_spheres": cnt["n_spheres"],
-                   "rays_per_frame": rays_per_frame, "kernel": "wavefront fp32" if use_wf else "per-pixel fp32 (AUTO, N <= 32)",
+        "config": workload_config(scene, W, H, segs, g, cnt),
+        "engine": {"kernel": "wavefront fp32" if use_wf else "per-pixel fp32 (AUTO, N <= 32)",
                    "partition": "single GPU" if world == 1 else (
                        f"interleaved {sr.S}-row stripes + " +
-                       ("peer-memory scatter kernel over NVLink (rtb_peer_scatter)" if sr.exchange == "p2p"
+                       ("peer-memory scatter kernel over NVLink (rtb_peer_scatter_group)" if sr.exchange == "p2p"
                         else "NCCL all-gather + de-interleave kernel") +
                        (f"; {sr.exchange_note}" if sr.exchange_note else "")),
-                   "frames_in_flight": fif,
-                   "l2": "per-frame working set (ray/node queues, ~2.7 GB) exceeds the 126 MB L2; no flush needed"},
+                   "frames_per_pass": G, "passes_in_flight": fif,
+                   "groups": mg.split_groups(args.steps, G)},
         "roofline": roofline,
         "e2e": {"value": round(e2e_value, 2), "unit": "Mrays/s", "ms_per_step": round(e2e_ms, 4),
                 "frames_per_s": round(1000.0 / e2e_ms, 3),

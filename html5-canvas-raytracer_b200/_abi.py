@@ -12,6 +12,7 @@ import os
 RTB_ABI_VERSION = 1
 RTB_MAX_LIGHTS = 4
 RTB_MAX_SEGS = 16
+RTB_MAX_GROUP = 8
 
 RTB_OK = 0
 RTB_ERR_INVALID, RTB_ERR_NO_DEVICE, RTB_ERR_CUDA, RTB_ERR_OOM = -1, -2, -3, -4
@@ -118,14 +119,15 @@ class RtbStats(C.Structure):
 # Every symbol include/rtb200.h declares; tests assert the built library exports all of them.
 EXPORTS = [
     "rtb_init", "rtb_shutdown", "rtb_scene_create", "rtb_scene_destroy", "rtb_scene_h2d_bytes", "rtb_finish", "rtb_set_frames_in_flight", "rtb_copy_status_device",
-    "rtb_peer_alloc", "rtb_peer_open", "rtb_peer_close", "rtb_peer_free", "rtb_peer_scatter", "rtb_peer_signal", "rtb_peer_wait", "rtb_render",
-    "rtb_render_device", "rtb_render_batch", "rtb_unstripe_device", "rtb_stripe_local_rows",
+    "rtb_peer_alloc", "rtb_peer_open", "rtb_peer_close", "rtb_peer_free", "rtb_peer_scatter", "rtb_peer_scatter_group", "rtb_peer_signal", "rtb_peer_wait", "rtb_render",
+    "rtb_render_device", "rtb_render_device_group", "rtb_render_batch", "rtb_unstripe_device", "rtb_stripe_local_rows",
     "rtb_stripe_padded_rows", "rtb_default_opts", "rtb_last_error", "rtb_version",
     "rtb_abi_version", "rtb_device_info",
 ]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "librtb200.so")
+# RTB200_LIB: another build of the SAME library (kernel experiments, tools/build_variant.py); never a fallback
+LIB_PATH = os.environ.get("RTB200_LIB") or os.path.join(_HERE, "csrc", "librtb200.so")
 _lib = None
 
 
@@ -163,6 +165,9 @@ def load() -> C.CDLL:
     lib.rtb_peer_scatter.argtypes = [vp, vpp, vpp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp,
                                      C.c_uint32, C.c_uint32, C.c_uint32, vp]
     lib.rtb_peer_scatter.restype = C.c_int
+    lib.rtb_peer_scatter_group.argtypes = [vp, C.c_uint64, C.c_int32, vpp, C.c_uint64, vpp, C.c_int32, C.c_int32,
+                                           C.c_int32, C.c_int32, C.c_int32, vp, C.c_uint32, C.c_uint32, C.c_uint32, vp]
+    lib.rtb_peer_scatter_group.restype = C.c_int
     lib.rtb_peer_signal.argtypes = [vpp, C.c_int32, C.c_int32, C.c_uint32, C.c_uint32, vp]; lib.rtb_peer_signal.restype = C.c_int
     lib.rtb_peer_wait.argtypes = [vp, C.c_int32, C.c_uint32, C.c_uint32, vp, vp]; lib.rtb_peer_wait.restype = C.c_int
     lib.rtb_copy_status_device.argtypes = [vp, vp, vp]; lib.rtb_copy_status_device.restype = C.c_int
@@ -170,6 +175,9 @@ def load() -> C.CDLL:
     lib.rtb_render.restype = C.c_int
     lib.rtb_render_device.argtypes = [vp, C.POINTER(RtbCamera), C.POINTER(RtbRenderOpts), vp, vp, C.POINTER(RtbStats)]
     lib.rtb_render_device.restype = C.c_int
+    lib.rtb_render_device_group.argtypes = [vp, C.POINTER(RtbCamera), C.c_int32, C.POINTER(RtbRenderOpts), vpp, vp,
+                                            C.POINTER(RtbStats)]
+    lib.rtb_render_device_group.restype = C.c_int
     lib.rtb_render_batch.argtypes = [vp, C.POINTER(RtbCamera), C.c_int32, C.POINTER(RtbRenderOpts), vp, C.POINTER(RtbStats)]
     lib.rtb_render_batch.restype = C.c_int
     lib.rtb_unstripe_device.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]

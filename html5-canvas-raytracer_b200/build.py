@@ -73,7 +73,7 @@ def build_library(force: bool = False, verbose: bool = False, ptxas_v: bool = Fa
                 sys.stdout.write(out)
             relink = True
     if relink or any(_mtime(o) > _mtime(LIB) for o in objs):
-        _run([nvcc, *ARCH, "-shared", "-o", LIB, *objs], verbose)
+        _run([nvcc, *ARCH, "-shared", "-o", LIB, *objs, "-ldl"], verbose)   # peer.cu: dlopen/dlsym (glibc < 2.34)
     return LIB
 
 

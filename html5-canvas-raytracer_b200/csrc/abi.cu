@@ -17,7 +17,7 @@ static thread_local char t_err[512] = "";
 // One render / scene operation at a time per process: the workspace, staging buffers and streams are
 // shared library state (the reference's caller is the single JS thread; this keeps other hosts safe).
 static std::recursive_mutex g_api_mutex;
-#define RTB_API_LOCK() std::lock_guard<std::recursive_mutex> api_lock_(g_api_mutex)
+std::recursive_mutex& rtb_api_mutex() { return g_api_mutex; }
 
 void rtb_set_error(const char* fmt, ...) {
   va_list ap;
@@ -128,6 +128,10 @@ int validate_render(const RtbScene_* s, const RtbCamera* cam, const RtbRenderOpt
   if (o->star_mode == RTB_STARS_STREAM) {
     if (!o->star_stream || o->star_stream_len == 0) { rtb_set_error("RTB_STARS_STREAM needs star_stream"); return RTB_ERR_INVALID; }
     const bool whole = o->y0 == 0 && (o->y1 <= 0 || o->y1 == cam->height) && o->stripe_world <= 1 && !o->out_packed;
+    if ((long long)cam->width * cam->height > 0x7fffffffll) {    // the raster-order scan counts pixels in an int
+      rtb_set_error("RTB_STARS_STREAM: canvas of %dx%d pixels exceeds 2^31 - 1", cam->width, cam->height);
+      return RTB_ERR_UNSUPPORTED;
+    }
     if (!whole || o->kernel == RTB_KERNEL_WAVEFRONT || o->precision != RTB_PRECISION_FP64) {
       rtb_set_error("RTB_STARS_STREAM replays the reference's call order: whole frames on the fp64 validation "
                     "kernel only (one differing hit/miss in fp32 would shift every later stream index)");
@@ -182,8 +186,19 @@ DevFrameT<T> make_frame(const RtbCamera* cam, const RtbRenderOpts* o) {
 
 // Launch the kernels of one frame into d_out on stream st.  Synchronises only on the wavefront path
 // (queue-overflow check) or when counters are wanted.
+int render_group_to_device(RtbScene_* s, const RtbCamera* cams, int n_frames, const RtbRenderOpts* o,
+                           uint8_t* const* d_outs, cudaStream_t st, RtbStats* stats, bool async);
+
 int render_to_device(RtbScene_* s, const RtbCamera* cam, const RtbRenderOpts* o, uint8_t* d_out,
                      cudaStream_t st, RtbStats* stats, bool async = false) {
+  return render_group_to_device(s, cam, 1, o, &d_out, st, stats, async);
+}
+
+// Frames of a group share the scene, the canvas size and the options; the wavefront path renders them in
+// one pass (wf_render), the per-pixel kernels one launch per frame.
+int render_group_to_device(RtbScene_* s, const RtbCamera* cams, int n_frames, const RtbRenderOpts* o,
+                           uint8_t* const* d_outs, cudaStream_t st, RtbStats* stats, bool async) {
+  const RtbCamera* cam = &cams[0];
   // Asynchronous frames may still be in flight.  A synchronous call collects them all; an asynchronous
   // one takes the next workspace slot and collects only the frame that used it last (with two frames in
   // flight that is the frame before the previous one, which therefore keeps running).  If a collected
@@ -216,8 +231,22 @@ int render_to_device(RtbScene_* s, const RtbCamera* cam, const RtbRenderOpts* o,
   uint32_t launches = 0;
   if (kernel == RTB_KERNEL_WAVEFRONT) {
     const DevFrameT<float> fr = make_frame<float>(cam, o);
-    return wf_render(s, cam, fr, rm, d_out, st, stats, async, slot);
+    return wf_render(s, cams, n_frames, fr, rm, d_outs, st, stats, async, slot);
   }
+  if (n_frames > 1) {                                      // per-pixel kernels: frame after frame
+    for (int f = 0; f < n_frames; f++) {
+      RtbStats one;
+      memset(&one, 0, sizeof one);
+      const int rc1 = render_group_to_device(s, &cams[f], 1, o, &d_outs[f], st, stats ? &one : nullptr, async);
+      if (rc1 != RTB_OK) return rc1;
+      if (stats) {
+        stats->nodes += one.nodes; stats->shadow_rays += one.shadow_rays; stats->sphere_tests += one.sphere_tests;
+        stats->launches += one.launches; stats->bands += one.bands;
+      }
+    }
+    return RTB_OK;
+  }
+  uint8_t* d_out = d_outs[0];
   unsigned long long* ctr = stats ? g_rtb.d_counters : nullptr;
   if (ctr) RTB_CUDA(cudaMemsetAsync(ctr, 0, 3 * sizeof(unsigned long long), st));
   int rc;
@@ -464,10 +493,8 @@ int rtb_scene_create(const RtbSceneDesc* d, rtb_scene_t* out) {
   size_t o_ltab[RTB_MAX_LIGHTS], o_lx[RTB_MAX_LIGHTS];
   for (int k = 0; k < d->n_lights; k++) { o_ltab[k] = take(tb); o_lx[k] = take(tb); }
   const size_t o_gtab = take(tb);
-  const size_t upload_bytes = off;                       // everything above is written by this call
-  size_t o_ptab[RTB_MAX_IN_FLIGHT], o_px[RTB_MAX_IN_FLIGHT];   // primary tables: filled per camera, one set
-  for (int i = 0; i < RTB_MAX_IN_FLIGHT; i++) { o_ptab[i] = take(tb); o_px[i] = take(tb); }   // per frame in flight
-  const size_t total = off;
+  const size_t upload_bytes = off;                       // everything is written by this call (the per-camera
+  const size_t total = off;                              // primary tables live in the workspace slots)
 
   if (g_rtb.cached_arena && g_rtb.cached_arena_bytes >= total) {
     s->arena = g_rtb.cached_arena; s->arena_bytes = g_rtb.cached_arena_bytes;
@@ -519,10 +546,8 @@ int rtb_scene_create(const RtbSceneDesc* d, rtb_scene_t* out) {
     s->d_light_x[k] = reinterpret_cast<float4*>(ds + o_lx[k]);
   }
   s->d_geom_tab = reinterpret_cast<float4*>(ds + o_gtab);
-  for (int i = 0; i < RTB_MAX_IN_FLIGHT; i++) {
-    s->d_primary_tab[i] = reinterpret_cast<float4*>(ds + o_ptab[i]);
-    s->d_primary_x[i] = reinterpret_cast<float4*>(ds + o_px[i]);
-  }
+  static uint64_t next_uid = 0;
+  s->uid = ++next_uid;
   fill_scene_view<double>(s->sc64, s, d, s->d_geom64, s->d_mtl64);
   fill_scene_view<float>(s->sc32, s, d, s->d_geom32, s->d_mtl32);
   guard.s = nullptr;
@@ -610,6 +635,41 @@ int rtb_render_device(rtb_scene_t s, const RtbCamera* cam, const RtbRenderOpts* 
   cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : g_rtb.stream;
   if (stats) { memset(stats, 0, sizeof *stats); RTB_CUDA(cudaEventRecord(g_rtb.ev0, st)); }
   rc = render_to_device(s, cam, o, (uint8_t*)d_out, st, stats, /*async=*/stats == nullptr);
+  if (rc != RTB_OK) return rc;
+  if (stats) {
+    RTB_CUDA(cudaEventRecord(g_rtb.ev1, st));
+    RTB_CUDA(cudaEventSynchronize(g_rtb.ev1));
+    float ms = 0;
+    RTB_CUDA(cudaEventElapsedTime(&ms, g_rtb.ev0, g_rtb.ev1));
+    stats->kernel_ms = ms;
+  }
+  return RTB_OK;
+}
+
+int rtb_render_device_group(rtb_scene_t s, const RtbCamera* cams, int32_t nframes, const RtbRenderOpts* o,
+                            void* const* d_outs, void* cuda_stream, RtbStats* stats) {
+  RTB_API_LOCK();
+  if (nframes < 1 || nframes > RTB_MAX_GROUP || !cams || !d_outs) {
+    rtb_set_error("a frame group holds 1..%d frames (got %d)", RTB_MAX_GROUP, nframes);
+    return RTB_ERR_INVALID;
+  }
+  int rc;
+  uint8_t* outs[RTB_MAX_GROUP];
+  for (int f = 0; f < nframes; f++) {
+    if ((rc = validate_render(s, &cams[f], o, d_outs[f])) != RTB_OK) return rc;
+    if (cams[f].width != cams[0].width || cams[f].height != cams[0].height) {
+      rtb_set_error("all frames of a group have the same size");
+      return RTB_ERR_UNSUPPORTED;
+    }
+    outs[f] = static_cast<uint8_t*>(d_outs[f]);
+  }
+  if (o->star_mode == RTB_STARS_STREAM && nframes > 1) {
+    rtb_set_error("RTB_STARS_STREAM renders one frame per call");
+    return RTB_ERR_UNSUPPORTED;
+  }
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : g_rtb.stream;
+  if (stats) { memset(stats, 0, sizeof *stats); RTB_CUDA(cudaEventRecord(g_rtb.ev0, st)); }
+  rc = render_group_to_device(s, cams, nframes, o, outs, st, stats, /*async=*/stats == nullptr);
   if (rc != RTB_OK) return rc;
   if (stats) {
     RTB_CUDA(cudaEventRecord(g_rtb.ev1, st));

@@ -16,6 +16,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <exception>
 #include <string>
 #include <vector>
 #include "rtb200.h"
@@ -143,6 +144,7 @@ napi_value Render(napi_env env, napi_callback_info info) {
     napi_value objects = prop(env, argv[0], "objects");
     uint32_t n = 0;
     NAPI_OK(napi_get_array_length(env, objects, &n));
+    if (n > (1u << 20)) throw Fail{"more than 2^20 spheres"};
     std::vector<RtbSphere> spheres(n);
     for (uint32_t i = 0; i < n; i++) {
       napi_value o, m;
@@ -172,7 +174,8 @@ napi_value Render(napi_env env, napi_callback_info info) {
       napi_value ts = prop(env, argv[0], "textures");
       uint32_t nt = 0;
       NAPI_OK(napi_get_array_length(env, ts, &nt));
-      textures.resize(nt);
+      if (nt > 4096) throw Fail{"more than 4096 textures"};       // the library's own limits, checked before
+      textures.resize(nt);                                          // anything is sized from JS-supplied numbers
       texel_store.resize(nt);
       for (uint32_t i = 0; i < nt; i++) {
         napi_value t;
@@ -180,6 +183,7 @@ napi_value Render(napi_env env, napi_callback_info info) {
         textures[i].width = (int32_t)num_prop(env, t, "width", 0, true);
         textures[i].height = (int32_t)num_prop(env, t, "height", 0, true);
         if (textures[i].width <= 0 || textures[i].height <= 0) throw Fail{"texture not loaded (width/height 0)"};
+        if (textures[i].width > 32768 || textures[i].height > 32768) throw Fail{"texture larger than 32768 x 32768"};
         read_texels(env, prop(env, t, "texels"), (size_t)textures[i].width * textures[i].height * 4, texel_store[i]);
         textures[i].texels = texel_store[i].data();
       }
@@ -265,6 +269,14 @@ napi_value Render(napi_env env, napi_callback_info info) {
   } catch (const Fail& f) {
     if (scene) rtb_scene_destroy(scene);
     napi_throw_error(env, nullptr, f.msg.c_str());          // JS `Error`; nothing crosses as a C++ exception
+    return undef;
+  } catch (const std::exception& e) {                       // std::bad_alloc / length_error of the staging vectors
+    if (scene) rtb_scene_destroy(scene);
+    napi_throw_error(env, nullptr, e.what());
+    return undef;
+  } catch (...) {
+    if (scene) rtb_scene_destroy(scene);
+    napi_throw_error(env, nullptr, "rtb200: unknown C++ exception");
     return undef;
   }
 }

@@ -26,17 +26,23 @@ struct PeerPtrs {
   void* p[RTB_MAX_PEERS];
 };
 
-// local packed rows -> every rank's frame.  One thread moves 16 bytes (4 pixels) to all peers.
+// local packed rows -> every rank's frame, for the n_frames frames of a group (frame f: local rows at
+// local + f * local_stride quads, destination frames.p[p] + f * frame_stride quads).  One thread moves
+// 16 bytes (4 pixels) to all peers.
 __global__ void __launch_bounds__(256)
 peer_scatter_kernel(const uint4* __restrict__ local, PeerPtrs frames, PeerPtrs ctl, int quads_per_row, int n_local,
-                    RowMap rm, int world, int rank, const uint32_t* __restrict__ status_word, uint32_t ready_off,
-                    uint32_t status_off, uint32_t seq, uint32_t* counter) {
-  const long long total = (long long)n_local * quads_per_row;
+                    int n_frames, size_t local_stride, size_t frame_stride, RowMap rm, int world, int rank,
+                    const uint32_t* __restrict__ status_word, uint32_t ready_off, uint32_t status_off, uint32_t seq,
+                    uint32_t* counter) {
+  const long long per_frame = (long long)n_local * quads_per_row;
+  const long long total = per_frame * n_frames;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    const int l = (int)(i / quads_per_row), q = (int)(i % quads_per_row);
-    const uint4 v = local[i];
-    const size_t dst = (size_t)rm.local_to_y(l) * quads_per_row + q;
+    const int f = (int)(i / per_frame);
+    const long long k = i - (long long)f * per_frame;
+    const int l = (int)(k / quads_per_row), q = (int)(k % quads_per_row);
+    const uint4 v = local[(size_t)f * local_stride + (size_t)k];
+    const size_t dst = (size_t)f * frame_stride + (size_t)rm.local_to_y(l) * quads_per_row + q;
 #pragma unroll 4
     for (int p = 0; p < world; p++) static_cast<uint4*>(frames.p[p])[dst] = v;
   }
@@ -122,6 +128,7 @@ int check_peers(int world, int rank) {
 extern "C" {
 
 int rtb_peer_alloc(uint64_t bytes, void** d_ptr, uint8_t* handle64) {
+  RTB_API_LOCK();
   if (!g_rtb.inited) { rtb_set_error("rtb_init() has not been called"); return RTB_ERR_NOT_INIT; }
   if (!d_ptr || !handle64 || bytes == 0) { rtb_set_error("NULL argument"); return RTB_ERR_INVALID; }
   static_assert(sizeof(cudaIpcMemHandle_t) == RTB_PEER_HANDLE_BYTES, "handle size");
@@ -142,6 +149,7 @@ int rtb_peer_alloc(uint64_t bytes, void** d_ptr, uint8_t* handle64) {
 }
 
 int rtb_peer_open(const uint8_t* handle64, void** d_ptr) {
+  RTB_API_LOCK();
   if (!g_rtb.inited) { rtb_set_error("rtb_init() has not been called"); return RTB_ERR_NOT_INIT; }
   if (!d_ptr || !handle64) { rtb_set_error("NULL argument"); return RTB_ERR_INVALID; }
   cudaIpcMemHandle_t h;
@@ -151,12 +159,14 @@ int rtb_peer_open(const uint8_t* handle64, void** d_ptr) {
 }
 
 int rtb_peer_close(void* d_ptr) {
+  RTB_API_LOCK();
   if (!d_ptr) return RTB_OK;
   RTB_CUDA(cudaIpcCloseMemHandle(d_ptr));
   return RTB_OK;
 }
 
 int rtb_peer_free(void* d_ptr) {
+  RTB_API_LOCK();
   if (!d_ptr) return RTB_OK;
   RTB_CUDA(cudaFree(d_ptr));
   return RTB_OK;
@@ -166,9 +176,20 @@ int rtb_peer_scatter(const void* d_local_packed, void* const* peer_frames, void*
                      int32_t height, int32_t stripe_rows, int32_t stripe_rank, int32_t stripe_world,
                      const void* d_status_u32, uint32_t ready_offset, uint32_t status_offset, uint32_t seq,
                      void* cuda_stream) {
+  return rtb_peer_scatter_group(d_local_packed, 0, 1, peer_frames, 0, peer_ctl, width, height, stripe_rows,
+                                stripe_rank, stripe_world, d_status_u32, ready_offset, status_offset, seq, cuda_stream);
+}
+
+int rtb_peer_scatter_group(const void* d_local_packed, uint64_t local_frame_stride_bytes, int32_t n_frames,
+                           void* const* peer_frames, uint64_t peer_frame_stride_bytes, void* const* peer_ctl,
+                           int32_t width, int32_t height, int32_t stripe_rows, int32_t stripe_rank,
+                           int32_t stripe_world, const void* d_status_u32, uint32_t ready_offset,
+                           uint32_t status_offset, uint32_t seq, void* cuda_stream) {
+  RTB_API_LOCK();
   int rc = check_peers(stripe_world, stripe_rank);
   if (rc != RTB_OK) return rc;
-  if (!d_local_packed || !peer_frames || !peer_ctl || width <= 0 || height <= 0 || stripe_rows <= 0) {
+  if (!d_local_packed || !peer_frames || !peer_ctl || width <= 0 || height <= 0 || stripe_rows <= 0 ||
+      n_frames < 1 || n_frames > RTB_MAX_GROUP || (local_frame_stride_bytes & 15u) || (peer_frame_stride_bytes & 15u)) {
     rtb_set_error("bad scatter arguments");
     return RTB_ERR_INVALID;
   }
@@ -191,11 +212,12 @@ int rtb_peer_scatter(const void* d_local_packed, void* const* peer_frames, void*
   // scatters of different frames may overlap on different streams: one election counter per sequence slot
   uint32_t* counter = g_rtb.d_peer_counter + (seq % RTB_MAX_IN_FLIGHT);
   const int quads = width / 4;
-  const long long total = (long long)n_local * quads;
+  const long long total = (long long)n_local * quads * n_frames;
   int grid = (int)std::min<long long>((total + 255) / 256, (long long)g_rtb.sm_count * 4);
   if (grid < 1) grid = 1;
-  peer_scatter_kernel<<<grid, 256, 0, st>>>(static_cast<const uint4*>(d_local_packed), fr, ct, quads, n_local, rm,
-                                            stripe_world, stripe_rank, static_cast<const uint32_t*>(d_status_u32),
+  peer_scatter_kernel<<<grid, 256, 0, st>>>(static_cast<const uint4*>(d_local_packed), fr, ct, quads, n_local, n_frames,
+                                            (size_t)(local_frame_stride_bytes / 16), (size_t)(peer_frame_stride_bytes / 16),
+                                            rm, stripe_world, stripe_rank, static_cast<const uint32_t*>(d_status_u32),
                                             ready_offset, status_offset, seq, counter);
   RTB_CUDA(cudaGetLastError());
   return RTB_OK;
@@ -203,6 +225,7 @@ int rtb_peer_scatter(const void* d_local_packed, void* const* peer_frames, void*
 
 int rtb_peer_signal(void* const* peer_ctl, int32_t world, int32_t rank, uint32_t word_offset, uint32_t value,
                     void* cuda_stream) {
+  RTB_API_LOCK();
   int rc = check_peers(world, rank);
   if (rc != RTB_OK) return rc;
   if (!peer_ctl) { rtb_set_error("NULL argument"); return RTB_ERR_INVALID; }
@@ -220,6 +243,7 @@ int rtb_peer_signal(void* const* peer_ctl, int32_t world, int32_t rank, uint32_t
 
 int rtb_peer_wait(const void* d_words_u32, int32_t n, uint32_t value, uint32_t timeout_ms, void* d_timeout_flag_u32,
                   void* cuda_stream) {
+  RTB_API_LOCK();
   if (!g_rtb.inited) { rtb_set_error("rtb_init() has not been called"); return RTB_ERR_NOT_INIT; }
   if (!d_words_u32 || !d_timeout_flag_u32 || n < 1 || n > 32) { rtb_set_error("bad wait arguments"); return RTB_ERR_INVALID; }
   cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : g_rtb.stream;

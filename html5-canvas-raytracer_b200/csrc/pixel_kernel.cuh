@@ -256,8 +256,8 @@ __device__ void trace_tree(const DevSceneT<T>& sc, const T* __restrict__ geom, c
 }
 
 // Primary ray main.js:186-193 for sub-sample (i,j) of a g x g stratified grid (g = 1: reference).
-template <typename T>
-RTB_DEVINL void primary_ray(const DevFrameT<T>& fr, int x, int y, int i, int j, T ray[3]) {
+template <typename T, typename F>   // F: DevFrameT<T> or the wavefront pipeline's per-frame camera
+RTB_DEVINL void primary_ray(const F& fr, int x, int y, int i, int j, T ray[3]) {
   const int g = fr.spp_grid;
   const T ox = (T(i) + T(0.5)) / T(g), oy = (T(j) + T(0.5)) / T(g);
   const T dist[3] = {T(x) - fr.projW + ox, fr.projH - T(y) - oy, fr.projD};

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <mutex>
 #include <string>
 #include <vector>
 #include "rtb_device.cuh"
@@ -18,6 +19,8 @@ struct WfCounters {          // one small device struct, zeroed per band
   uint32_t level_end[RTB_MAX_SEGS + 1];   // level L = [level_end[L-1], level_end[L]); level_end[0] = 0
   uint32_t sq_count[RTB_MAX_LIGHTS];      // shadow queue fill per light
   uint32_t work_trace[RTB_MAX_SEGS + 2];   // next chunk of level L (persistent-kernel work counters)
+  uint32_t work_primary[RTB_MAX_GROUP];    // level 1: one counter pair per run of frames sharing a camera origin
+  uint32_t work_primary_tail[RTB_MAX_GROUP];
   uint32_t work_shadow[RTB_MAX_LIGHTS];
   uint32_t work_trace_tail[RTB_MAX_SEGS + 2];   // small-chunk tail phase of the same launches
   uint32_t work_shadow_tail[RTB_MAX_LIGHTS];
@@ -64,14 +67,10 @@ struct RtbScene_ {
   float4* d_geom_tab = nullptr;           // packed general-ray table (wf_make_geom_table)
   float4* d_light_tab[RTB_MAX_LIGHTS] = {nullptr, nullptr, nullptr, nullptr};   // packed, per light
   float4* d_light_x[RTB_MAX_LIGHTS] = {nullptr, nullptr, nullptr, nullptr};     // exact (L, c), per light
-  // per camera origin, one set per frame in flight (WfSlot): two frames of a moving camera may overlap
-  float4* d_primary_tab[RTB_MAX_IN_FLIGHT] = {};   // packed
-  float4* d_primary_x[RTB_MAX_IN_FLIGHT] = {};     // exact (L, c)
+  uint64_t uid = 0;                       // never reused: keys the per-slot primary-table cache (WfSlot)
   char* arena = nullptr;                  // single device allocation all the pointers above point into
   size_t arena_bytes = 0;
   size_t h2d_bytes = 0;                   // bytes rtb_scene_create uploaded
-  double primary_origin[RTB_MAX_IN_FLIGHT][3] = {};
-  bool primary_valid[RTB_MAX_IN_FLIGHT] = {};
   // asynchronous device renders (rtb_render_device without stats): the queue-overflow verdict of the
   // last enqueued frame is collected by rtb_finish() / the next call on the library
   int wf_rows_hint = 0;                   // band size known to fit (0 = none yet)
@@ -88,8 +87,14 @@ struct WfSlot {
   cudaStream_t stream2 = nullptr;             // overlapped early shadow pass
   cudaEvent_t ev_primary = nullptr, ev_early = nullptr, ev_async = nullptr;
   void* h_sticky = nullptr;                   // pinned: overflow flag + device counters of the last call
-  char* h_tab = nullptr;                      // pinned staging of the per-camera primary tables
-  size_t h_tab_bytes = 0;
+  // per-camera-origin primary tables of the slot's frame group (packed + exact, RTB_MAX_GROUP sets), their
+  // pinned staging, and what each set currently holds (scene uid, padded size, origin)
+  char* d_ptab = nullptr;
+  char* h_tab = nullptr;
+  size_t ptab_bytes = 0;
+  uint64_t tab_scene[RTB_MAX_GROUP] = {};
+  int tab_n_pad[RTB_MAX_GROUP] = {};
+  double tab_origin[RTB_MAX_GROUP][3] = {};
   RtbScene_* pending_scene = nullptr;         // scene with an asynchronous frame in flight in this slot
   int pending_rows = 0;                       // band size of that frame
 };
@@ -128,6 +133,10 @@ struct RtbGlobal {
 extern RtbGlobal g_rtb;
 
 void rtb_set_error(const char* fmt, ...);
+// One render / scene / peer operation at a time per process: workspaces, staging buffers, streams and the
+// lazily created peer counters are shared library state.
+std::recursive_mutex& rtb_api_mutex();
+#define RTB_API_LOCK() std::lock_guard<std::recursive_mutex> api_lock_(rtb_api_mutex())
 #define RTB_CUDA(call)                                                                     \
   do {                                                                                     \
     cudaError_t e_ = (call);                                                               \
@@ -203,8 +212,9 @@ inline void wf_make_geom_table(const RtbSphere* sp, int n, int n_pad, float4* ta
 
 // wavefront pipeline: renders the rows of `rm` into d_out, splitting into bands as needed.
 // async = true: enqueue only; the overflow check is deferred to rtb_finish_pending().
-int wf_render(RtbScene_* s, const RtbCamera* cam, const DevFrameT<float>& fr, const RowMap& rm,
-              uint8_t* d_out, cudaStream_t st, RtbStats* stats, bool async, int slot);
+// `cams` / `d_outs`: the n_frames (<= RTB_MAX_GROUP) frames of one group - same scene, size and options.
+int wf_render(RtbScene_* s, const RtbCamera* cams, int n_frames, const DevFrameT<float>& fr, const RowMap& rm,
+              uint8_t* const* d_outs, cudaStream_t st, RtbStats* stats, bool async, int slot);
 // Wait for the asynchronous frame in flight in `slot` (-1: in every slot, oldest first) and file its
 // verdict in its scene.
 int rtb_finish_pending(int slot);

@@ -46,26 +46,45 @@ struct WfSticky {             // survives across bands of one call
   unsigned long long nodes, shadow_rays, sphere_tests;
 };
 
+// One camera of a frame group (the closure variables spanish() reads, main.js:85-105), fp64: primary rays
+// are generated in fp64 and rounded once.  Field names are those primary_ray<>() reads.
+struct WfCam {
+  double origin[3], axisX[3], axisY[3], axisZ[3];
+  double projW, projH, projD;
+  int32_t spp_grid, camera_mode;
+};
+
+// A wavefront pass renders the same row band of n_frames frames of a sequence at once (a FRAME GROUP):
+// level 1 holds the primary rays of all of them, frame by frame, and every later level, shadow queue and
+// compose pass is shared - so that the kernels of a striped multi-GPU frame (1/world of the rows) are as
+// large as those of a whole frame.  Frames of a group share scene, size and options; cameras may differ.
 struct WfParams {
   DevSceneT<float> sc;
-  DevFrameT<double> fr64;     // primary rays are generated in fp64 and rounded once
+  DevFrameT<double> fr64;     // size / options shared by the group (camera fields unused: see cam[])
+  WfCam cam[RTB_MAX_GROUP];
+  float origin32[RTB_MAX_GROUP][3];   // camera origins rounded once (ray origins of level 1)
+  uint8_t* out[RTB_MAX_GROUP];   // one framebuffer per frame
   RowMap rm;
   WfBuffers b;
   WfSticky* sticky;
   const float4* geom;         // exact Cx, Cy, Cz, r2                                  (n_spheres)
   // packed sweep tables (see wf_make_table): per sphere PAIR two float4, padded with never-hit dummies
   const float4* geom_tab;     // (x0,x1,y0,y1) (z0,z1,-r2_0',-r2_1')
-  const float4* primary_tab;  // (Lx0,Lx1,Ly0,Ly1) (Lz0,Lz1,sc0,sc1), L = C - origin
+  // primary tables, one per run of consecutive frames that share a camera origin:
+  const float4* primary_tab[RTB_MAX_GROUP];  // (Lx0,Lx1,Ly0,Ly1) (Lz0,Lz1,sc0,sc1), L = C - origin
+  const float4* primary_x[RTB_MAX_GROUP];    // exact (L, |L|^2 - r2) for the slow path  (n_spheres)
   const float4* light_tab[RTB_MAX_LIGHTS];
-  const float4* primary_x;    // exact (L, |L|^2 - r2) for the slow path               (n_spheres)
   const float4* light_x[RTB_MAX_LIGHTS];
   int32_t n_pad;
-  float origin[3];
+  int32_t n_frames;           // frames in the group (1 .. RTB_MAX_GROUP)
+  int32_t n_runs;             // origin runs; run g = frames [run_begin[g], run_begin[g + 1])
+  int32_t run_begin[RTB_MAX_GROUP + 1];
   int32_t band_l0;            // first local row of the band
   int32_t band_rows;
-  uint32_t n_sub;             // band_rows * W * spp  == number of level-1 nodes
+  uint32_t n_sub_frame;       // band_rows * W * spp == level-1 nodes of ONE frame
+  uint32_t n_sub;             // n_frames * n_sub_frame == number of level-1 nodes
   int32_t spp;                // g*g
-  int32_t aligned4;           // W % 4 == 0 and output 16-byte aligned: uint4 stores
+  int32_t aligned4;           // W % 4 == 0 and outputs 16-byte aligned: uint4 stores
   int32_t fixed_r;            // 0: rays per lane from the cost model; 1/2/3: always R, R/2, R/4 and no guided tail
 };
 
@@ -380,8 +399,9 @@ __device__ __noinline__ void process_hit(const WfParams& P, const WfRay& r, unsi
       }
       uint32_t px = 0, py = 0, sub = 0;
       if (m.sampler_kind == RTB_SAMPLER_STARS && P.fr64.star_mode == RTB_STARS_HASH) {
-        const uint32_t pix = r.pixsub / (uint32_t)P.spp;   // star hash key: pixel, sub-sample, path
-        sub = r.pixsub - pix * (uint32_t)P.spp;
+        const uint32_t in_frame = r.pixsub % P.n_sub_frame;   // star hash key: pixel, sub-sample, path
+        const uint32_t pix = in_frame / (uint32_t)P.spp;
+        sub = in_frame - pix * (uint32_t)P.spp;
         px = pix % (uint32_t)W;
         py = (uint32_t)P.rm.local_to_y(P.band_l0 + (int)(pix / (uint32_t)W));
       }
@@ -461,6 +481,27 @@ __device__ __noinline__ void process_hit(const WfParams& P, const WfRay& r, unsi
   }
 }
 
+// ---- RAYGEN ---------------------------------------------------------------------------------------------
+// Primary rays of the band (main.js:186-193) for every frame of the group, generated in fp64 with the
+// frame's own camera and rounded ONCE; direction stored in ray_o[node] (level-1 entries of the ray arrays
+// are otherwise unused).  A kernel of its own: one thread per ray at full occupancy, which keeps the fp64
+// division / square-root code and the per-frame camera loads out of the register-bound sweep kernel.
+__global__ void __launch_bounds__(WF_THREADS)
+wf_raygen_kernel(const __grid_constant__ WfParams P) {
+  const int W = P.fr64.width;
+  const int g = P.fr64.spp_grid;
+  for (uint32_t node = blockIdx.x * blockDim.x + threadIdx.x; node < P.n_sub; node += gridDim.x * blockDim.x) {
+    const uint32_t f = node / P.n_sub_frame;               // frame of the group
+    const uint32_t in_frame = node - f * P.n_sub_frame;
+    const uint32_t pix = in_frame / (uint32_t)P.spp;
+    const uint32_t sub = in_frame - pix * (uint32_t)P.spp;
+    const int lrow = P.band_l0 + (int)(pix / (uint32_t)W);
+    double ray[3];
+    primary_ray<double>(P.cam[f], (int)(pix % (uint32_t)W), P.rm.local_to_y(lrow), (int)(sub % g), (int)(sub / g), ray);
+    P.b.ray_o[node] = make_float4((float)ray[0], (float)ray[1], (float)ray[2], 0.f);
+  }
+}
+
 // ---- TRACE ----------------------------------------------------------------------------------------------
 // Rays per lane are a launch-time decision made on the device from the size of the level: R_SHARED /
 // R_GENERAL when the level fills the machine several times over, half or a quarter of that for small
@@ -501,14 +542,8 @@ template <bool PRIMARY>
 RTB_DEVINL void ray_setup(const WfParams& P, uint32_t node, float (&a)[3], float (&b)[3], float& nku, float& nkv,
                           int& self) {
   if (PRIMARY) {
-    const int W = P.fr64.width;
-    const uint32_t pix = node / (uint32_t)P.spp;
-    const uint32_t sub = node - pix * (uint32_t)P.spp;
-    const int lrow = P.band_l0 + (int)(pix / (uint32_t)W);
-    const int g = P.fr64.spp_grid;
-    double ray[3];
-    primary_ray<double>(P.fr64, (int)(pix % (uint32_t)W), P.rm.local_to_y(lrow), (int)(sub % g), (int)(sub / g), ray);
-    a[0] = -(float)ray[0]; a[1] = -(float)ray[1]; a[2] = -(float)ray[2];
+    const float4 d = P.b.ray_o[node];                      // written by wf_raygen_kernel
+    a[0] = -d.x; a[1] = -d.y; a[2] = -d.z;
   } else {
     const float4 ro = P.b.ray_o[node], rd = P.b.ray_d[node];
     self = __float_as_int(P.b.pos[P.b.link[node].x].w);
@@ -531,9 +566,12 @@ RTB_DEVINL WfRay ray_record(const WfParams& P, uint32_t node, bool active, float
   r.node = node;
   r.active = active;
   r.path = 1; r.pixsub = node; r.segs_left = P.fr64.segs;
-  r.o[0] = P.origin[0]; r.o[1] = P.origin[1]; r.o[2] = P.origin[2];
+  r.o[0] = r.o[1] = r.o[2] = 0.f;
   r.d[0] = -ndx; r.d[1] = -ndy; r.d[2] = -ndz;
-  if (!PRIMARY) {
+  if (PRIMARY) {
+    const float* o = P.origin32[min(node / P.n_sub_frame, (uint32_t)(RTB_MAX_GROUP - 1))];
+    r.o[0] = o[0]; r.o[1] = o[1]; r.o[2] = o[2];
+  } else {
     r.d[0] = r.d[1] = r.d[2] = 0.f;
     if (active) {
       const float4 ro = P.b.ray_o[node], rd = P.b.ray_d[node];
@@ -552,7 +590,8 @@ RTB_DEVINL WfRay ray_record(const WfParams& P, uint32_t node, bool active, float
 // are pulled per warp.
 template <bool PRIMARY, int R>
 RTB_DEVINL void trace_chunks(const WfParams& P, uint32_t* work, uint32_t first, const float4* __restrict__ tab,
-                             uint32_t begin, uint32_t end, uint32_t lane, unsigned long long& my_nodes) {
+                             const float4* __restrict__ exact, uint32_t begin, uint32_t end, uint32_t lane,
+                             unsigned long long& my_nodes) {
   const int n_pad = P.n_pad;
   const float eps = P.sc.eps;
   constexpr uint32_t CHUNK = 32u * R;
@@ -582,7 +621,7 @@ RTB_DEVINL void trace_chunks(const WfParams& P, uint32_t* work, uint32_t first, 
         ray_setup<PRIMARY>(P, node, a[q], b[q], nku[q], nkv[q], self[q]);
       }
     }
-    if (PRIMARY) sweep_primary<R>(tab, P.primary_x, 0, n_pad, a, active, best, eps);
+    if (PRIMARY) sweep_primary<R>(tab, exact, 0, n_pad, a, active, best, eps);
     else sweep_general<R>(tab, P.geom, P.b.ray_o, P.b.ray_d, 0, n_pad, a, b, nku, nkv, nodes, self, active, best, eps);
     __syncwarp();
 #pragma unroll
@@ -591,31 +630,50 @@ RTB_DEVINL void trace_chunks(const WfParams& P, uint32_t* work, uint32_t first, 
   }
 }
 
+// One contiguous range of rays that share a sweep table: a whole level of general rays, or the primary rays
+// of one run of frames with a common camera origin.  Contains CTA barriers: called by all threads.
 template <bool PRIMARY>
-__global__ void __launch_bounds__(WF_THREADS, WF_MIN_CTAS)
-wf_trace_kernel(const __grid_constant__ WfParams P, int level) {
+RTB_DEVINL void trace_range(const WfParams& P, float4* tab, const float4* __restrict__ src,
+                            const float4* __restrict__ exact, uint32_t begin, uint32_t end, uint32_t* wa,
+                            uint32_t* wt, uint32_t lane, unsigned long long& my_nodes) {
   constexpr int RB = PRIMARY ? R_SHARED : R_GENERAL;
-  extern __shared__ float4 tab[];
-  const int n = P.sc.n_spheres, n_pad = P.n_pad;
-  uint32_t begin, end;
-  level_range(P, level, begin, end);
-  const uint32_t lane = threadIdx.x & 31u;
-  unsigned long long my_nodes = 0;
-  uint32_t* wa = &P.b.ctr->work_trace[level];
-  uint32_t* wt = &P.b.ctr->work_trace_tail[level];
+  const int n_pad = P.n_pad;
   const int r = P.fixed_r ? (RB >> (P.fixed_r - 1)) : pick_rays_per_lane(end - begin, RB, PRIMARY ? 9u : 20u);
   const uint32_t split = P.fixed_r ? end : end - tail_rays(end - begin, r, RB / 4);
   const uint32_t first = cta_claim(wa);
-  // a CTA whose claim lies beyond the level has nothing to do: leave at once (the slot goes to the
+  // a CTA whose claim lies beyond the range has nothing to do: leave at once (the slot goes to the
   // kernels of the other frames in flight) without even loading the table
   if ((uint64_t)begin + (uint64_t)(first - (threadIdx.x >> 5)) * (32u * (uint32_t)r) < split || split < end) {
-    const float4* src = PRIMARY ? P.primary_tab : P.geom_tab;
     for (int i = threadIdx.x; i < n_pad; i += blockDim.x) tab[i] = src[i];
     __syncthreads();
-    if (r == RB) trace_chunks<PRIMARY, RB>(P, wa, first, tab, begin, split, lane, my_nodes);
-    else if (r == RB / 2) trace_chunks<PRIMARY, RB / 2>(P, wa, first, tab, begin, split, lane, my_nodes);
-    else trace_chunks<PRIMARY, RB / 4>(P, wa, first, tab, begin, split, lane, my_nodes);
-    if (split < end) trace_chunks<PRIMARY, RB / 4>(P, wt, next_chunk(wt, lane), tab, split, end, lane, my_nodes);
+    if (r == RB) trace_chunks<PRIMARY, RB>(P, wa, first, tab, exact, begin, split, lane, my_nodes);
+    else if (r == RB / 2) trace_chunks<PRIMARY, RB / 2>(P, wa, first, tab, exact, begin, split, lane, my_nodes);
+    else trace_chunks<PRIMARY, RB / 4>(P, wa, first, tab, exact, begin, split, lane, my_nodes);
+    if (split < end) trace_chunks<PRIMARY, RB / 4>(P, wt, next_chunk(wt, lane), tab, exact, split, end, lane, my_nodes);
+  }
+}
+
+template <bool PRIMARY>
+__global__ void __launch_bounds__(WF_THREADS, WF_MIN_CTAS)
+wf_trace_kernel(const __grid_constant__ WfParams P, int level) {
+  extern __shared__ float4 tab[];
+  const int n = P.sc.n_spheres;
+  const uint32_t lane = threadIdx.x & 31u;
+  unsigned long long my_nodes = 0;
+  if (PRIMARY) {
+    // level 1: the frames of the group, run by run (frames of a run share the camera origin, hence the
+    // table); a CTA moves on to the next run while others still finish the previous one
+    for (int g = 0; g < P.n_runs; g++) {
+      if (g > 0) __syncthreads();                          // table and claim word are reused
+      trace_range<true>(P, tab, P.primary_tab[g], P.primary_x[g], (uint32_t)P.run_begin[g] * P.n_sub_frame,
+                        (uint32_t)P.run_begin[g + 1] * P.n_sub_frame, &P.b.ctr->work_primary[g],
+                        &P.b.ctr->work_primary_tail[g], lane, my_nodes);
+    }
+  } else {
+    uint32_t begin, end;
+    level_range(P, level, begin, end);
+    trace_range<false>(P, tab, P.geom_tab, nullptr, begin, end, &P.b.ctr->work_trace[level],
+                       &P.b.ctr->work_trace_tail[level], lane, my_nodes);
   }
   // stats
   for (int o2 = 16; o2 > 0; o2 >>= 1) my_nodes += __shfl_down_sync(0xffffffffu, my_nodes, o2);
@@ -812,15 +870,18 @@ wf_compose_kernel(const __grid_constant__ WfParams P, int level) {
 }
 
 // Level 1: average the sub-samples of each pixel, quantise as a Uint8ClampedArray store would
-// (main.js:195-198) and write 4 pixels per thread as one uint4.
+// (main.js:195-198) and write 4 pixels per thread as one uint4 - for every frame of the group.
 __global__ void __launch_bounds__(WF_THREADS)
-wf_resolve_kernel(const __grid_constant__ WfParams P, uint8_t* __restrict__ out) {
+wf_resolve_kernel(const __grid_constant__ WfParams P) {
   const int W = P.fr64.width;
   const int groups_per_row = (W + 3) / 4;
-  const long long total = (long long)P.band_rows * groups_per_row;
+  const long long per_frame = (long long)P.band_rows * groups_per_row;
+  const long long total = per_frame * P.n_frames;
   for (long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x; gi < total;
        gi += (long long)gridDim.x * blockDim.x) {
-    const int r = (int)(gi / groups_per_row), x0 = (int)(gi % groups_per_row) * 4;
+    const int f = (int)(gi / per_frame);
+    const long long gf = gi - (long long)f * per_frame;
+    const int r = (int)(gf / groups_per_row), x0 = (int)(gf % groups_per_row) * 4;
     const int lrow = P.band_l0 + r;
     uint32_t packed[4] = {0u, 0u, 0u, 0u};
     const int nx = min(4, W - x0);
@@ -829,7 +890,7 @@ wf_resolve_kernel(const __grid_constant__ WfParams P, uint8_t* __restrict__ out)
       float acc[3] = {0.f, 0.f, 0.f};
       for (int s = 0; s < P.spp; s++) {
         float col[3];
-        node_colour(P, pix * (uint32_t)P.spp + (uint32_t)s, col);
+        node_colour(P, (uint32_t)f * P.n_sub_frame + pix * (uint32_t)P.spp + (uint32_t)s, col);
         if (P.spp == 1) { acc[0] = col[0]; acc[1] = col[1]; acc[2] = col[2]; }
         else { acc[0] += col[0]; acc[1] += col[1]; acc[2] += col[2]; }
       }
@@ -837,7 +898,7 @@ wf_resolve_kernel(const __grid_constant__ WfParams P, uint8_t* __restrict__ out)
       packed[i] = clamped_u8(255.f * acc[0]) | (clamped_u8(255.f * acc[1]) << 8) |
                   (clamped_u8(255.f * acc[2]) << 16) | (255u << 24);
     }
-    uint32_t* row = reinterpret_cast<uint32_t*>(out) + P.rm.out_row(lrow) * (size_t)W;
+    uint32_t* row = reinterpret_cast<uint32_t*>(P.out[f]) + P.rm.out_row(lrow) * (size_t)W;
     if (P.aligned4 && nx == 4) {
       *reinterpret_cast<uint4*>(row + x0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
     } else {
@@ -906,6 +967,7 @@ void wf_free() {
     if (sl.ev_async) cudaEventDestroy(sl.ev_async);
     if (sl.h_sticky) cudaFreeHost(sl.h_sticky);
     if (sl.h_tab) cudaFreeHost(sl.h_tab);
+    if (sl.d_ptab) cudaFree(sl.d_ptab);
     sl = WfSlot{};
   }
 }
@@ -939,14 +1001,16 @@ int rtb_finish_pending(int slot) {
   return RTB_OK;
 }
 
-int wf_render(RtbScene_* s, const RtbCamera* cam, const DevFrameT<float>& fr32, const RowMap& rm,
-              uint8_t* d_out, cudaStream_t st, RtbStats* stats, bool async, int slot) {
+int wf_render(RtbScene_* s, const RtbCamera* cams, int n_frames, const DevFrameT<float>& fr32, const RowMap& rm,
+              uint8_t* const* d_outs, cudaStream_t st, RtbStats* stats, bool async, int slot) {
   if (stats) async = false;
-  const int ps = slot % RTB_MAX_IN_FLIGHT;                 // also the primary-table set of this slot
+  const int ps = slot % RTB_MAX_IN_FLIGHT;
   WfSlot& sl = g_rtb.slot[ps];
+  const RtbCamera* cam = &cams[0];                         // size and options are common to the group
   const int W = cam->width;
   const int n_rows = rm.n_local();
-  if (n_rows <= 0) return RTB_OK;
+  if (n_rows <= 0 || n_frames <= 0) return RTB_OK;
+  if (n_frames > RTB_MAX_GROUP) { rtb_set_error("a frame group holds at most %d frames", RTB_MAX_GROUP); return RTB_ERR_INVALID; }
   const int n = s->n_spheres;
   const int n_pad = s->n_pad;
   const size_t smem = (size_t)n_pad * sizeof(float4);
@@ -960,32 +1024,54 @@ int wf_render(RtbScene_* s, const RtbCamera* cam, const DevFrameT<float>& fr32, 
     return RTB_ERR_UNSUPPORTED;
   }
 
-  // primary tables: per-sphere constants of rays leaving the camera origin, in fp64, rounded once
-  // (one table set and one pinned staging buffer per slot: the slot's previous frame has been collected
-  // before it is reused, so neither is still being read and no host wait is needed here)
-  if (!s->primary_valid[ps] || s->primary_origin[ps][0] != cam->origin[0] ||
-      s->primary_origin[ps][1] != cam->origin[1] || s->primary_origin[ps][2] != cam->origin[2]) {
-    if (sl.h_tab_bytes < 2 * smem) {
-      if (sl.h_tab) { RTB_CUDA(cudaDeviceSynchronize()); cudaFreeHost(sl.h_tab); }
-      sl.h_tab = nullptr; sl.h_tab_bytes = 0;
-      RTB_CUDA(cudaMallocHost(&sl.h_tab, 2 * smem));
-      sl.h_tab_bytes = 2 * smem;
+  WfParams P;
+  memset(&P, 0, sizeof P);
+
+  // primary tables: per-sphere constants of rays leaving a camera origin, in fp64, rounded once; one table
+  // per run of consecutive frames with the same origin (a fixed camera: one run).  Tables and their pinned
+  // staging belong to the workspace slot: the slot's previous pass has been collected before it is reused,
+  // so neither is still being read and no host wait is needed here.  Cached per (scene, origin).
+  {
+    const size_t need = (size_t)RTB_MAX_GROUP * 2 * smem;
+    if (sl.ptab_bytes < need) {
+      if (sl.d_ptab) { RTB_CUDA(cudaDeviceSynchronize()); cudaFree(sl.d_ptab); cudaFreeHost(sl.h_tab); }
+      sl.d_ptab = nullptr; sl.h_tab = nullptr; sl.ptab_bytes = 0;
+      RTB_CUDA(cudaMalloc(&sl.d_ptab, need));
+      RTB_CUDA(cudaMallocHost(&sl.h_tab, need));
+      sl.ptab_bytes = need;
+      for (int g = 0; g < RTB_MAX_GROUP; g++) sl.tab_scene[g] = 0;
     }
-    float4* h_tab = reinterpret_cast<float4*>(sl.h_tab);
-    float4* h_x = h_tab + n_pad;
-    wf_make_table(s->spheres.data(), n, n_pad, cam->origin, h_tab, h_x);
-    RTB_CUDA(cudaMemcpyAsync(s->d_primary_tab[ps], h_tab, smem, cudaMemcpyHostToDevice, st));
-    RTB_CUDA(cudaMemcpyAsync(s->d_primary_x[ps], h_x, smem, cudaMemcpyHostToDevice, st));
-    if (!async) RTB_CUDA(cudaStreamSynchronize(st));      // synchronous calls may come back on another stream
-    for (int c = 0; c < 3; c++) s->primary_origin[ps][c] = cam->origin[c];
-    s->primary_valid[ps] = true;
+    int n_runs = 0;
+    bool uploaded = false;
+    for (int f = 0; f < n_frames; f++) {
+      const double* o = cams[f].origin;
+      if (f > 0 && o[0] == cams[f - 1].origin[0] && o[1] == cams[f - 1].origin[1] && o[2] == cams[f - 1].origin[2]) continue;
+      const int g = n_runs++;
+      P.run_begin[g] = f;
+      float4* d_tab = reinterpret_cast<float4*>(sl.d_ptab + (size_t)g * 2 * smem);
+      float4* d_x = d_tab + n_pad;
+      if (sl.tab_scene[g] != s->uid || sl.tab_n_pad[g] != n_pad || sl.tab_origin[g][0] != o[0] ||
+          sl.tab_origin[g][1] != o[1] || sl.tab_origin[g][2] != o[2]) {
+        float4* h_tab = reinterpret_cast<float4*>(sl.h_tab + (size_t)g * 2 * smem);
+        wf_make_table(s->spheres.data(), n, n_pad, o, h_tab, h_tab + n_pad);
+        RTB_CUDA(cudaMemcpyAsync(d_tab, h_tab, 2 * smem, cudaMemcpyHostToDevice, st));
+        uploaded = true;
+        sl.tab_scene[g] = s->uid; sl.tab_n_pad[g] = n_pad;
+        for (int c = 0; c < 3; c++) sl.tab_origin[g][c] = o[c];
+      }
+      P.primary_tab[g] = d_tab;
+      P.primary_x[g] = d_x;
+    }
+    P.run_begin[n_runs] = n_frames;
+    P.n_runs = n_runs;
+    if (uploaded && !async) RTB_CUDA(cudaStreamSynchronize(st));   // synchronous calls may come back on another stream
   }
 
   const int g = fr32.spp_grid, spp = g * g;
-  const uint64_t sub_per_row = (uint64_t)W * spp;
-  const uint64_t n_sub_frame = sub_per_row * (uint64_t)n_rows;
+  const uint64_t sub_per_row = (uint64_t)W * spp * (uint64_t)n_frames;   // level-1 nodes per band row, all frames
+  const uint64_t n_sub_total = sub_per_row * (uint64_t)n_rows;
   // queue capacity: room for ~2 extra nodes per primary ray, bounded; RTB_WF_CAP_NODES overrides (tests)
-  uint64_t cap = std::min<uint64_t>(std::max<uint64_t>(3 * n_sub_frame, 1u << 20), 1u << 25);
+  uint64_t cap = std::min<uint64_t>(std::max<uint64_t>(3 * n_sub_total, 1u << 20), 1u << 25);
   if (const char* e = getenv("RTB_WF_CAP_NODES")) { const long long v = atoll(e); if (v > 0) cap = (uint64_t)v; }
   if (cap < 4 * sub_per_row) cap = 4 * sub_per_row;      // at least one row per band with headroom
   if (cap > 0xfffffff0ull) { rtb_set_error("frame too wide for the wavefront queues"); return RTB_ERR_UNSUPPORTED; }
@@ -994,18 +1080,29 @@ int wf_render(RtbScene_* s, const RtbCamera* cam, const DevFrameT<float>& fr32, 
   // the shared workspace may be larger than this call asked for; band sizes and the overflow
   // check follow the REQUESTED capacity so that results do not depend on earlier calls
 
-  WfParams P;
-  memset(&P, 0, sizeof P);
   P.sc = s->sc32;
-  // fp64 camera for primary rays
+  // fp64 cameras for the primary rays
   DevFrameT<double>& f = P.fr64;
   f.width = cam->width; f.height = cam->height; f.segs = fr32.segs; f.spp_grid = g;
   f.star_mode = fr32.star_mode; f.camera_mode = cam->camera_mode; f.star_seed = fr32.star_seed;
   for (int c = 0; c < 3; c++) {
     f.origin[c] = cam->origin[c]; f.axisX[c] = cam->axisX[c]; f.axisY[c] = cam->axisY[c]; f.axisZ[c] = cam->axisZ[c];
-    P.origin[c] = (float)cam->origin[c];
   }
   f.projW = cam->projW; f.projH = cam->projH; f.projD = cam->projD;
+  bool aligned = (W % 4 == 0);
+  for (int i = 0; i < n_frames; i++) {
+    WfCam& c = P.cam[i];
+    for (int k = 0; k < 3; k++) {
+      c.origin[k] = cams[i].origin[k]; c.axisX[k] = cams[i].axisX[k];
+      c.axisY[k] = cams[i].axisY[k]; c.axisZ[k] = cams[i].axisZ[k];
+    }
+    c.projW = cams[i].projW; c.projH = cams[i].projH; c.projD = cams[i].projD;
+    c.spp_grid = g; c.camera_mode = cams[i].camera_mode;
+    for (int k = 0; k < 3; k++) P.origin32[i][k] = (float)cams[i].origin[k];
+    P.out[i] = d_outs[i];
+    aligned = aligned && ((reinterpret_cast<uintptr_t>(d_outs[i]) & 15u) == 0);
+  }
+  P.n_frames = n_frames;
   P.rm = rm;
   P.b = sl.wf;
   P.b.cap_nodes = (uint32_t)cap;
@@ -1013,16 +1110,14 @@ int wf_render(RtbScene_* s, const RtbCamera* cam, const DevFrameT<float>& fr32, 
   P.sticky = reinterpret_cast<WfSticky*>(reinterpret_cast<char*>(sl.wf.ctr) + sizeof(WfCounters));
   P.geom = reinterpret_cast<const float4*>(s->d_geom32);
   P.geom_tab = s->d_geom_tab;
-  P.primary_tab = s->d_primary_tab[ps];
-  P.primary_x = s->d_primary_x[ps];
   for (int k = 0; k < s->n_lights; k++) { P.light_tab[k] = s->d_light_tab[k]; P.light_x[k] = s->d_light_x[k]; }
   P.n_pad = n_pad;
   P.spp = spp;
-  P.aligned4 = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_out) & 15u) == 0);
+  P.aligned4 = aligned ? 1 : 0;
   {
     static int fixed_r = -1;
     if (fixed_r < 0) { const char* e = getenv("RTB_WF_FIXED_R"); fixed_r = e ? std::max(0, std::min(3, atoi(e))) : 0; }
-    // Three or more frames in flight: other frames' kernels fill this frame's tails, so the chunk size
+    // Three or more passes in flight: other passes' kernels fill this one's tails, so the chunk size
     // that is cheapest per ray wins over the one that ends a lone launch soonest (measured, 1/8 of a 4K
     // frame per GPU: 1.37 -> 1.28 ms per frame).
     P.fixed_r = fixed_r ? fixed_r : (async && g_rtb.frames_in_flight >= 3 ? 1 : 0);
@@ -1078,11 +1173,13 @@ int wf_render(RtbScene_* s, const RtbCamera* cam, const DevFrameT<float>& fr32, 
       P.band_l0 = l0;
       P.band_rows = std::min(rows_per_band, n_rows - l0);
       P.n_sub = (uint32_t)((uint64_t)P.band_rows * sub_per_row);
+      P.n_sub_frame = P.n_sub / (uint32_t)n_frames;
       bands++;
       RTB_CUDA(cudaMemsetAsync(sl.wf.ctr, 0, sizeof(WfCounters), st));
       if ((rc = mark(T_START)) != RTB_OK) return rc;
+      wf_raygen_kernel<<<grid_c, WF_THREADS, 0, st>>>(P);
       wf_trace_kernel<true><<<grid_p, WF_THREADS, smem, st>>>(P, 1);
-      launches++;
+      launches += 2;
       if ((rc = mark(T_PRIMARY)) != RTB_OK) return rc;
       // Without instrumentation the light-0 sweep of the level-1 nodes runs on a second stream,
       // concurrently with the secondary trace levels (independent work; fills their tails).
@@ -1109,7 +1206,7 @@ int wf_render(RtbScene_* s, const RtbCamera* cam, const DevFrameT<float>& fr32, 
         wf_compose_kernel<<<grid_c, WF_THREADS, 0, st>>>(P, L);
         launches++;
       }
-      wf_resolve_kernel<<<grid_c, WF_THREADS, 0, st>>>(P, d_out);
+      wf_resolve_kernel<<<grid_c, WF_THREADS, 0, st>>>(P);
       launches++;
       if ((rc = mark(T_COMPOSE)) != RTB_OK) return rc;
       RTB_CUDA(cudaGetLastError());

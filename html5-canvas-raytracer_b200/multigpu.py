@@ -26,15 +26,34 @@ from .scene import make_opts
 DEFAULT_STRIPE_ROWS = 1      # measured on the 4K / 1024-sphere frame at 8 ranks: the per-rank node counts spread by
                              # 0.24 % with single rows, 0.6 % with 2, 2 % with 4, 5 % with 8 rows per stripe, and
                              # the slowest rank's frame time falls from 1.660 ms (4) to 1.617 ms (1)
-MAX_IN_FLIGHT = 8            # = RTB_MAX_IN_FLIGHT of the library
-DEFAULT_IN_FLIGHT = 4        # frames redraw_sequence keeps in flight on one GPU (measured, one rank's eighth of a 4K
-                             # frame on one B200: 1.67 / 1.41 / 1.28 / 1.25 / 1.24 ms per frame for 1 / 2 / 3 / 4 / 8)
-DEFAULT_IN_FLIGHT_MULTI = 8  # ... with world > 1: the exchange adds latency to hide and a rank's share of a frame is
-                             # small (8 GPUs, 4K: 1.383 ms per frame with 4 in flight, 1.351 with 8)
+MAX_IN_FLIGHT = 8            # = RTB_MAX_IN_FLIGHT of the library: wavefront passes that may overlap on one GPU
+MAX_GROUP = A.RTB_MAX_GROUP  # frames one wavefront pass renders together (rtb_render_device_group)
+DEFAULT_IN_FLIGHT = 4        # passes redraw_sequence keeps in flight on one GPU (measured, 4K frames on one B200:
+                             # 9.58 ms per frame with one in flight, 9.16 with four)
+DEFAULT_IN_FLIGHT_MULTI = 3  # ... with world > 1, where a pass is a GROUP of `world` frames: each rank renders 1/world
+                             # of every frame, so a group is a whole frame's worth of rays per pass; the second pass in
+                             # flight hides the exchange and fills the tails of the first
+MAX_REPEATS = 64             # frames re-rendered because of ray-queue overflows before giving up (as rtb_render_batch)
 
 
 def default_in_flight(world: int) -> int:
     return DEFAULT_IN_FLIGHT if world <= 1 else DEFAULT_IN_FLIGHT_MULTI
+
+
+def default_group(world: int) -> int:
+    """Frames per wavefront pass in sequence mode: with the rows of a frame dealt over `world` GPUs, `world`
+    frames per pass give every kernel launch the size it has on a single GPU."""
+    return max(1, min(world, MAX_GROUP))
+
+
+def split_groups(n: int, group: int) -> List[int]:
+    """Sizes of the frame groups of an n-frame sequence: as few groups of at most `group` frames as possible,
+    evened out (20 frames, group 8 -> 7, 7, 6)."""
+    if n <= 0:
+        return []
+    k = -(-n // max(1, group))
+    base, rem = divmod(n, k)
+    return [base + 1] * rem + [base] * (k - rem)
 
 
 # ---- partition arithmetic (mirrors RowMap in csrc/rtb_device.cuh; tested against it) ----------------
@@ -102,18 +121,22 @@ class StripedRenderer:
     """Row-stripe sharded redraw(): every rank ends up with the full framebuffer on its GPU.
 
     exchange = "p2p" (default on GPUs): each rank stores its packed stripe rows straight into every rank's
-    framebuffer over NVLink with one kernel of the library (rtb_peer_scatter: all-gather + de-interleave in
+    framebuffer over NVLink with one kernel of the library (rtb_peer_scatter_group: all-gather + de-interleave in
     one pass, no collective library in the data path, nothing spins while holding SMs); sequence numbers
     and per-rank status words travel in a small control block.  Buffers are shared with CUDA IPC handles
     exchanged once over torch.distributed.
-    exchange = "nccl": `all_gather_into_tensor` of [padded_rows + 1][W][4] per rank — the packed stripe rows
-    plus one trailer row whose first word is the rank's status — followed by rtb_unstripe_device.
+    exchange = "nccl": `all_gather_into_tensor` of [group][padded_rows + 1][W][4] per rank — the packed stripe
+    rows of every frame of the group plus one trailer row each, whose first word (frame 0) is the rank's
+    status — followed by rtb_unstripe_device per frame.
     Either way a non-zero status word (that rank's ray queues overflowed) reaches every rank with the
-    frame, so all ranks take the same repeat decision without a second exchange.
-    "auto" tries p2p and falls back to nccl when the ranks cannot map each other's memory."""
+    frames, so all ranks take the same repeat decision without a second exchange.
+    "auto" tries p2p and falls back to nccl when the ranks cannot map each other's memory.
+
+    Sequences (redraw_sequence) are rendered in GROUPS of `group` frames per wavefront pass
+    (rtb_render_device_group; default = world), `slots` passes in flight."""
 
     def __init__(self, renderer, width: int, height: int, rank: int, world: int,
-                 stripe_rows: int = DEFAULT_STRIPE_ROWS, exchange: str = "auto"):
+                 stripe_rows: int = DEFAULT_STRIPE_ROWS, exchange: str = "auto", group: int = 0, slots: int = 0):
         import torch
 
         self.r, self.W, self.H = renderer, width, height
@@ -124,8 +147,9 @@ class StripedRenderer:
         self.stride = self.padded + 1
         dev = torch.device("cuda", torch.cuda.current_device())
         self.dev = dev
-        # MAX_IN_FLIGHT sets of everything: redraw_sequence keeps several frames in flight
-        K = MAX_IN_FLIGHT
+        self.G = G = max(1, min(MAX_GROUP, int(group) or default_group(world)))
+        # `slots` sets of everything: redraw_sequence keeps several passes in flight
+        self.K = K = max(1, min(MAX_IN_FLIGHT, int(slots) or (MAX_IN_FLIGHT if G == 1 else max(3, default_in_flight(world)))))
         self.flags_host = [torch.zeros((max(world, 1) + 1,), dtype=torch.int32).pin_memory() for _ in range(K)]
         self.status_dev = torch.zeros((K, 4), dtype=torch.int32, device=dev)      # world == 1: status words
         self._streams = None
@@ -133,7 +157,7 @@ class StripedRenderer:
         self.exchange_note = ""
         self._peer = None
         if world > 1:
-            self.local = [torch.zeros((self.stride, width, 4), dtype=torch.uint8, device=dev) for _ in range(K)]
+            self.local = [torch.zeros((G, self.stride, width, 4), dtype=torch.uint8, device=dev) for _ in range(K)]
             if exchange not in ("auto", "p2p", "nccl"):
                 raise ValueError(f"exchange must be auto, p2p or nccl (got {exchange!r})")
             if exchange in ("auto", "p2p"):
@@ -146,10 +170,11 @@ class StripedRenderer:
                     self.exchange_note = f"p2p unavailable ({err})"
             if self.exchange != "p2p":
                 self.exchange = "nccl"
-                self.gathered = [torch.empty((world, self.stride, width, 4), dtype=torch.uint8, device=dev) for _ in range(K)]
+                self.gathered = [torch.empty((world, G, self.stride, width, 4), dtype=torch.uint8, device=dev)
+                                 for _ in range(K)]
         if self.exchange != "p2p":
-            self.frames = [torch.empty((height, width, 4), dtype=torch.uint8, device=dev) for _ in range(K)]
-        self.frame = self.frames[0]
+            self.frames = [torch.empty((G, height, width, 4), dtype=torch.uint8, device=dev) for _ in range(K)]
+        self.frame = self.frames[0][0]
 
     # -- peer-memory exchange: set-up ----------------------------------------------------------------------
     def _setup_p2p(self):
@@ -158,7 +183,7 @@ class StripedRenderer:
         import torch
         import torch.distributed as dist
 
-        K, world = MAX_IN_FLIGHT, self.world
+        K, G, world = self.K, self.G, self.world
         if world > 16 or self.W % 4 != 0:
             return "needs world <= 16 and a width that is a multiple of 4"
         frame_bytes = self.H * self.W * 4
@@ -166,7 +191,7 @@ class StripedRenderer:
         handles = {k: (C.c_uint8 * 64)() for k in own}
         err = None
         try:
-            A.check(self.lib.rtb_peer_alloc(K * frame_bytes, C.byref(own["frames"]), handles["frames"]))
+            A.check(self.lib.rtb_peer_alloc(K * G * frame_bytes, C.byref(own["frames"]), handles["frames"]))
             A.check(self.lib.rtb_peer_alloc(_CTL_WORDS * 4, C.byref(own["ctl"]), handles["ctl"]))
         except A.RtbError as e:
             err = str(e)
@@ -205,13 +230,14 @@ class StripedRenderer:
             return err or "a peer could not map this rank's buffers"
         VP = C.c_void_p * world
         self._peer = {
-            "own": own, "opened": opened,
-            "frames": [VP(*[bases["frames"][p] + k * frame_bytes for p in range(world)]) for k in range(K)],
+            "own": own, "opened": opened, "frame_bytes": frame_bytes,
+            # per slot: every rank's first framebuffer of that slot (the group's frames follow contiguously)
+            "frames": [VP(*[bases["frames"][p] + k * G * frame_bytes for p in range(world)]) for k in range(K)],
             "ctl": VP(*bases["ctl"]),
             "ctl_base": own["ctl"].value,
             "seq": 0, "slot_seq": [0] * K, "unacked": [0] * K,
         }
-        self.frames = [torch.as_tensor(_DeviceBytes(own["frames"].value + k * frame_bytes, (self.H, self.W, 4)),
+        self.frames = [torch.as_tensor(_DeviceBytes(own["frames"].value + k * G * frame_bytes, (G, self.H, self.W, 4)),
                                        device=self.dev) for k in range(K)]
         self._ctl = torch.as_tensor(_DeviceBytes(own["ctl"].value, (_CTL_WORDS,), "<i4"), device=self.dev)
         return None
@@ -234,36 +260,43 @@ class StripedRenderer:
         self.frames = []
 
     # -- building blocks (everything is enqueued on the CURRENT torch stream) --------------------------
-    def _enqueue_render(self, camera, slot, stats, kw):
+    def _enqueue_render(self, cams, slot, stats, kw):
+        """One wavefront pass for the frames `cams` (a group) into slot `slot`."""
         import torch
 
         stream = torch.cuda.current_stream().cuda_stream
+        n = len(cams)
         if self.world <= 1:
-            self.r.redraw_device(camera, make_opts(**kw), self.frames[slot].data_ptr(), stream, stats)
+            outs = [self.frames[slot][b].data_ptr() for b in range(n)]
+            self.r.redraw_device_group(cams, make_opts(**kw), outs, stream, stats)
             A.check(self.lib.rtb_copy_status_device(self.r._h, self.status_dev[slot].data_ptr(), A.stream_arg(stream)))
             return
         o = make_opts(stripe_rows=self.S, stripe_rank=self.rank, stripe_world=self.world, out_packed=1, **kw)
         loc = self.local[slot]
-        self.r.redraw_device(camera, o, loc.data_ptr(), stream, stats)
-        A.check(self.lib.rtb_copy_status_device(self.r._h, loc[self.padded].data_ptr(), A.stream_arg(stream)))
+        self.r.redraw_device_group(cams, o, [loc[b].data_ptr() for b in range(n)], stream, stats)
+        A.check(self.lib.rtb_copy_status_device(self.r._h, loc[0, self.padded].data_ptr(), A.stream_arg(stream)))
 
     def _enqueue_gather(self, slot):
         import torch.distributed as dist
 
         # concatenated-along-dim-0 view: the form both NCCL and gloo accept
-        return dist.all_gather_into_tensor(self.gathered[slot].view(-1, self.W, 4), self.local[slot], async_op=True)
+        return dist.all_gather_into_tensor(self.gathered[slot].view(-1, self.W, 4), self.local[slot].view(-1, self.W, 4),
+                                           async_op=True)
 
-    def _enqueue_unstripe(self, slot):
+    def _enqueue_unstripe(self, slot, n):
         import torch
 
         stream = torch.cuda.current_stream().cuda_stream
-        A.check(self.lib.rtb_unstripe_device(self.gathered[slot].data_ptr(), self.frames[slot].data_ptr(), self.W,
-                                             self.H, self.S, self.world, self.stride, A.stream_arg(stream)))
-        flags = self.gathered[slot][:, self.padded, 0, :].contiguous().view(torch.int32).view(-1)
+        for b in range(n):
+            # frame b of every rank sits at [rank][b]; rank stride = G * stride rows
+            A.check(self.lib.rtb_unstripe_device(self.gathered[slot][0, b].data_ptr(), self.frames[slot][b].data_ptr(),
+                                                 self.W, self.H, self.S, self.world, self.G * self.stride,
+                                                 A.stream_arg(stream)))
+        flags = self.gathered[slot][:, 0, self.padded, 0, :].contiguous().view(torch.int32).view(-1)
         self.flags_host[slot][:self.world].copy_(flags, non_blocking=True)
 
     def _enqueue_release(self, slot):
-        """p2p: tell every peer that this rank no longer reads framebuffer `slot` (its previous frame)."""
+        """p2p: tell every peer that this rank no longer reads the framebuffers of `slot` (its previous group)."""
         import torch
 
         P = self._peer
@@ -272,9 +305,9 @@ class StripedRenderer:
             A.check(self.lib.rtb_peer_signal(P["ctl"], self.world, self.rank, _CTL_ACK + 16 * slot, P["unacked"][slot], st))
             P["unacked"][slot] = 0
 
-    def _enqueue_scatter(self, slot):
-        """p2p: wait until every peer has released framebuffer `slot`, store this rank's rows into all of
-        them, wait until every rank's rows of this frame have arrived here."""
+    def _enqueue_scatter(self, slot, n):
+        """p2p: wait until every peer has released the framebuffers of `slot`, store this rank's rows of the
+        group's n frames into all of them, wait until every rank's rows have arrived here."""
         import torch
 
         P = self._peer
@@ -286,10 +319,12 @@ class StripedRenderer:
         if prev:
             A.check(self.lib.rtb_peer_wait(C.c_void_p(ctl + 4 * (_CTL_ACK + 16 * slot)), self.world, prev,
                                            _PEER_TIMEOUT_MS, tflag, st))
-        A.check(self.lib.rtb_peer_scatter(C.c_void_p(self.local[slot].data_ptr()), P["frames"][slot], P["ctl"], self.W,
-                                          self.H, self.S, self.rank, self.world,
-                                          C.c_void_p(self.local[slot][self.padded].data_ptr()),
-                                          _CTL_READY + 16 * slot, _CTL_STATUS + 16 * slot, seq, st))
+        loc = self.local[slot]
+        A.check(self.lib.rtb_peer_scatter_group(C.c_void_p(loc.data_ptr()), self.stride * self.W * 4, n,
+                                                P["frames"][slot], P["frame_bytes"], P["ctl"], self.W, self.H,
+                                                self.S, self.rank, self.world,
+                                                C.c_void_p(loc[0, self.padded].data_ptr()),
+                                                _CTL_READY + 16 * slot, _CTL_STATUS + 16 * slot, seq, st))
         A.check(self.lib.rtb_peer_wait(C.c_void_p(ctl + 4 * (_CTL_READY + 16 * slot)), self.world, seq,
                                        _PEER_TIMEOUT_MS, tflag, st))
         P["slot_seq"][slot] = seq
@@ -298,55 +333,71 @@ class StripedRenderer:
         self.flags_host[slot][:self.world].copy_(self._ctl[s0:s0 + self.world], non_blocking=True)
         self.flags_host[slot][self.world:].copy_(self._ctl[_CTL_TIMEOUT:_CTL_TIMEOUT + 1], non_blocking=True)
 
-    def _enqueue_frame(self, camera, slot, kw, stats=None):
-        """Render + exchange of one frame into self.frames[slot]; status words to the host."""
+    def _enqueue_group(self, cams, slot, kw, stats=None):
+        """Render + exchange of one group of frames into self.frames[slot][0..n); status words to the host."""
+        n = len(cams)
+        if n > self.G:
+            raise ValueError(f"group of {n} frames exceeds this renderer's group size {self.G}")
         if self.exchange == "p2p":
             self._enqueue_release(slot)
-        self._enqueue_render(camera, slot, stats, kw)
+        self._enqueue_render(cams, slot, stats, kw)
         if self.exchange == "p2p":
-            self._enqueue_scatter(slot)
+            self._enqueue_scatter(slot, n)
         elif self.exchange == "nccl":
             self._enqueue_gather(slot).wait()             # stream-level wait, the host does not block
-            self._enqueue_unstripe(slot)
+            self._enqueue_unstripe(slot, n)
         else:
             self.flags_host[slot][:1].copy_(self.status_dev[slot, :1], non_blocking=True)
 
     def _frame_ok(self, slot) -> bool:
-        """Host side, after the frame's stream work has completed: did every rank render it validly?"""
+        """Host side, after the group's stream work has completed: did every rank render it validly?"""
         f = self.flags_host[slot]
         if self.exchange == "p2p" and int(f[self.world]) != 0:
             raise RuntimeError("peer exchange timed out: a rank stopped publishing frames")
         return not bool(f[:max(self.world, 1)].any())
+
+    @staticmethod
+    def _overflow_error():
+        return A.RtbError(A.RTB_ERR_OVERFLOW, f"a frame still overflows its ray queues after {MAX_REPEATS} attempts "
+                                              "(one-row bands do not fit the queue capacity)")
 
     # -- one frame (latency mode) ----------------------------------------------------------------------
     def redraw(self, camera, stats=None, **kw):
         """Render this rank's stripes, exchange, return the device framebuffer (valid until the next call).
         Everything is only ENQUEUED; the host waits once.  If any rank's ray queues overflowed, every
         rank sees that in the status words and repeats the frame (the library has shrunk the offending
-        rank's bands, deterministically)."""
+        rank's bands, deterministically) - at most MAX_REPEATS times, then RtbError(RTB_ERR_OVERFLOW)."""
+        return self.redraw_group([camera], stats, **kw)[0]
+
+    def redraw_group(self, cameras, stats=None, **kw):
+        """The same for a group of up to `group` frames in ONE wavefront pass; returns the [n, H, W, 4] device view."""
         import torch
 
-        while True:
-            self._enqueue_frame(camera, 0, kw, stats)
+        for _ in range(MAX_REPEATS):
+            self._enqueue_group(list(cameras), 0, kw, stats)
             torch.cuda.current_stream().synchronize()
             self.r.finish()                               # clears the library's pending state (already complete)
             if self._frame_ok(0):
-                self.frame = self.frames[0]
-                return self.frame
+                self.frame = self.frames[0][0]
+                return self.frames[0][:len(cameras)]
+        raise self._overflow_error()
 
     # -- a sequence of frames (throughput mode) ----------------------------------------------------------
-    def redraw_sequence(self, cameras, on_frame=None, frames_in_flight: int = 0, **kw):
-        """Software-pipelined: up to `frames_in_flight` (1..8; 0 = default_in_flight(world)) frames are enqueued before the host waits
-        for the oldest one, each on its own stream with its own library workspace.  Later frames render
-        while frame i is in the collective, and the kernels of the frames interleave on the GPU: the
-        short per-level launches of one fill the tails of the others.  `on_frame(i, frame)` is called
-        (device tensor, valid for the next frames_in_flight - 1 calls) once frame i is assembled on this
-        rank.  Returns the number of frames that had to be repeated because of queue overflows (every
-        rank reads the same gathered status words, so every rank repeats the same frames)."""
+    def redraw_sequence(self, cameras, on_frame=None, frames_in_flight: int = 0, group: int = 0, **kw):
+        """Software-pipelined: the sequence is cut into groups of up to `group` frames (0 = this renderer's group
+        size; one wavefront pass each) and up to `frames_in_flight` passes (0 = default_in_flight(world)) are
+        enqueued before the host waits for the oldest one, each on its own stream with its own library workspace.
+        Later groups render while group i is in the exchange, and the kernels of the passes interleave on the
+        GPU.  `on_frame(i, frame)` is called (device tensor, valid until `frames_in_flight - 1` further groups
+        have been issued) once frame i is assembled on this rank.  Returns the number of groups that had to be
+        repeated because of queue overflows (every rank reads the same status words, so every rank repeats the
+        same groups); more than MAX_REPEATS raise RtbError(RTB_ERR_OVERFLOW)."""
         import torch
 
-        depth = max(1, min(MAX_IN_FLIGHT, int(frames_in_flight) or default_in_flight(self.world)))
-        n = len(cameras)
+        depth = max(1, min(self.K, int(frames_in_flight) or default_in_flight(self.world)))
+        sizes = split_groups(len(cameras), max(1, min(self.G, int(group) or self.G)))
+        starts = [sum(sizes[:i]) for i in range(len(sizes))]
+        n = len(sizes)
         main = torch.cuda.current_stream()
         if self._streams is None:
             self._streams = [torch.cuda.Stream(device=self.dev) for _ in range(MAX_IN_FLIGHT)]
@@ -362,24 +413,27 @@ class StripedRenderer:
                 while i < n and len(inflight) < depth:
                     slot = i % depth
                     with torch.cuda.stream(self._streams[slot]):
-                        self._enqueue_frame(cameras[i], slot, kw)
+                        self._enqueue_group(cameras[starts[i]:starts[i] + sizes[i]], slot, kw)
                         done[slot].record()
                     inflight.append(i)
                     i += 1
                 j = inflight.pop(0)
                 jslot = j % depth
-                done[jslot].synchronize()                 # the host waits for frame j only
+                done[jslot].synchronize()                 # the host waits for group j only
                 if not self._frame_ok(jslot):             # same words on every rank: same decision everywhere
                     repeats += 1
+                    if repeats > MAX_REPEATS:
+                        raise self._overflow_error()
                     for st in self._streams:
                         st.synchronize()
-                    self.r.finish()                       # collects every frame in flight; bands were shrunk
-                    i, inflight = j, []                   # restart the pipeline at frame j
+                    self.r.finish()                       # collects every pass in flight; bands were shrunk
+                    i, inflight = j, []                   # restart the pipeline at group j
                     continue
-                self.frame = self.frames[jslot]
+                self.frame = self.frames[jslot][sizes[j] - 1]
                 if on_frame:
                     with torch.cuda.stream(self._streams[jslot]):
-                        on_frame(j, self.frame)
+                        for b in range(sizes[j]):
+                            on_frame(starts[j] + b, self.frames[jslot][b])
         finally:
             for st in self._streams:
                 st.synchronize()
@@ -413,13 +467,24 @@ class FrameBatchRenderer:
 
         stream = torch.cuda.current_stream().cuda_stream
         f = first + self.rank
+
+        def render_valid(r):
+            # An asynchronous wavefront frame may come back invalid (ray queues overflowed; the library has
+            # then shrunk its bands).  Collect the verdict and re-render HERE, before the collective: every
+            # rank enters the all-gather exactly once, with a valid frame, whatever happened on the others.
+            for _ in range(MAX_REPEATS):
+                r.redraw_device(cameras[f], make_opts(**kw), self.mine.data_ptr(), stream, stats)
+                torch.cuda.current_stream().synchronize()
+                if r.finish():
+                    return
+            raise StripedRenderer._overflow_error()
+
         if f < len(cameras):
             if objects_for_frame is not None:
                 with Renderer(objects_for_frame(f), device=torch.cuda.current_device()) as r:
-                    r.redraw_device(cameras[f], make_opts(**kw), self.mine.data_ptr(), stream, stats)
-                    torch.cuda.current_stream().synchronize()
+                    render_valid(r)
             else:
-                self.r.redraw_device(cameras[f], make_opts(**kw), self.mine.data_ptr(), stream, stats)
+                render_valid(self.r)
         if self.world <= 1:
             self.step[0].copy_(self.mine)
         else:

@@ -78,6 +78,19 @@ class Renderer:
                                             A.stream_arg(stream),
                                             C.byref(stats) if stats is not None else None))
 
+    def redraw_device_group(self, cameras, opts, device_ptrs, stream=None,
+                            stats: Optional[A.RtbStats] = None) -> None:
+        """A GROUP of up to RTB_MAX_GROUP frames (same size and options, one camera and one device buffer each)
+        in one pass of the wavefront pipeline (rtb_render_device_group)."""
+        cams = [self._cam(c) for c in cameras]
+        n = len(cams)
+        if n != len(device_ptrs):
+            raise ValueError("one device buffer per camera")
+        arr = (A.RtbCamera * n)(*cams)
+        ptrs = (C.c_void_p * n)(*[int(p) for p in device_ptrs])
+        A.check(self._lib.rtb_render_device_group(self._h, arr, n, C.byref(opts), ptrs, A.stream_arg(stream),
+                                                  C.byref(stats) if stats is not None else None))
+
     def finish(self) -> bool:
         """Collect the verdict of the last asynchronous redraw_device().  True: the frame is valid.
         False: its ray queues overflowed - the library has shrunk its bands; issue the same call again."""
@@ -98,8 +111,13 @@ class Renderer:
         n = len(cams)
         arr = (A.RtbCamera * max(n, 1))(*cams)
         o = opts if opts is not None else make_opts(**kw)
+        if any(c.width != cams[0].width or c.height != cams[0].height for c in cams):
+            raise ValueError("all frames of a batch have the same size")
         if out is None:
             out = np.zeros((n, cams[0].height, cams[0].width, 4), np.uint8) if n else np.zeros((0, 0, 0, 4), np.uint8)
+        need = n * cams[0].width * cams[0].height * 4 if n else 0
+        if out.dtype != np.uint8 or not out.flags["C_CONTIGUOUS"] or out.size < need:
+            raise ValueError("out must be a C-contiguous uint8 buffer of nframes*width*height*4 bytes")
         st = A.RtbStats()
         A.check(self._lib.rtb_render_batch(self._h, arr, n, C.byref(o), out.ctypes.data,
                                            C.byref(st) if stats else None))

@@ -34,6 +34,7 @@ extern "C" {
 #define RTB_ABI_VERSION 1u
 #define RTB_MAX_LIGHTS 4      /* main.js:283 lists 2 live + 2 commented-out lights */
 #define RTB_MAX_SEGS 16       /* recursion depth literal is 8 at main.js:194 */
+#define RTB_MAX_GROUP 8       /* frames rendered by one pass of the wavefront pipeline (rtb_render_device_group) */
 
 /* ---- error codes --------------------------------------------------------------------------- */
 enum {
@@ -202,6 +203,18 @@ int rtb_render(rtb_scene_t scene, const RtbCamera* cam, const RtbRenderOpts* opt
 int rtb_render_device(rtb_scene_t scene, const RtbCamera* cam, const RtbRenderOpts* opts,
                       void* d_out_rgba8, void* cuda_stream, RtbStats* stats_or_null);
 
+/* A frame GROUP on the device: nframes (1 .. RTB_MAX_GROUP) frames of a sequence - same scene, canvas size
+ * and options; one camera and one device framebuffer (or packed stripe buffer) each - rendered by ONE pass
+ * of the wavefront pipeline: the primary rays of all frames form level 1 and every later recursion level,
+ * shadow queue and compose pass is shared.  A rank of an N-GPU row-striped sequence renders 1/N of every
+ * frame; grouping N frames makes its kernels as large as those of a whole frame (no short launches, N
+ * times fewer of them).  Otherwise exactly rtb_render_device: enqueue-only without stats, one verdict
+ * (rtb_finish / rtb_copy_status_device) for the whole group.  Per-pixel kernels (RTB_KERNEL_PIXEL, or AUTO
+ * on small scenes) render the frames one after the other.
+ * Replaces: nframes consecutive redraw() calls of an animation loop around main.js:180-199. */
+int rtb_render_device_group(rtb_scene_t scene, const RtbCamera* cams, int32_t nframes, const RtbRenderOpts* opts,
+                            void* const* d_out_rgba8, void* cuda_stream, RtbStats* stats_or_null);
+
 /* Wait for the scene's asynchronous frame (if any).  RTB_OK: the frame is valid.  RTB_ERR_OVERFLOW: its
  * ray queues overflowed and the frame is INVALID; the library has already reduced the band size, so
  * issuing the same rtb_render_device call again succeeds (deterministic).  A verdict that was never
@@ -263,6 +276,14 @@ int rtb_peer_scatter(const void* d_local_packed, void* const* peer_frames, void*
                      int32_t height, int32_t stripe_rows, int32_t stripe_rank, int32_t stripe_world,
                      const void* d_status_u32, uint32_t ready_offset, uint32_t status_offset, uint32_t seq,
                      void* cuda_stream);
+/* The same for the n_frames frames of a group in ONE kernel: frame f's packed rows start at d_local_packed +
+ * f * local_frame_stride_bytes and go to peer_frames[p] + f * peer_frame_stride_bytes on every peer p (both
+ * strides multiples of 16); one status word and one sequence number for the whole group. */
+int rtb_peer_scatter_group(const void* d_local_packed, uint64_t local_frame_stride_bytes, int32_t n_frames,
+                           void* const* peer_frames, uint64_t peer_frame_stride_bytes, void* const* peer_ctl,
+                           int32_t width, int32_t height, int32_t stripe_rows, int32_t stripe_rank,
+                           int32_t stripe_world, const void* d_status_u32, uint32_t ready_offset,
+                           uint32_t status_offset, uint32_t seq, void* cuda_stream);
 int rtb_peer_signal(void* const* peer_ctl, int32_t world, int32_t rank, uint32_t word_offset, uint32_t value,
                     void* cuda_stream);
 int rtb_peer_wait(const void* d_words_u32, int32_t n, uint32_t value, uint32_t timeout_ms, void* d_timeout_flag_u32,
