@@ -53,20 +53,28 @@ def measured_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """SM clock + throttle reasons during the timed region (NVML; nvidia-smi as fallback)."""
+    """SM clocks + throttle reasons of the job's GPUs under load (NVML), polled by ONE thread on rank 0.
+    NOT inside the timed region: at N = 8 every NVML query stalls the peer-memory exchange for milliseconds
+    (measured, 20 frames: 23.5 ms without polling, 27.1 ms with every rank polling its GPU, 29.0 ms with rank
+    0 polling all eight - profiles/r02_notes.md).  The clock the timed region ran at is measured on the
+    device instead (rtb_clock_probe before and after it: SM cycles / ns); this thread covers the phases right
+    after it - the per-class pass and the end-to-end passes, GPUs busy throughout - plus one sample taken
+    immediately before the region."""
 
-    def __init__(self, index=0, period=0.01):
+    def __init__(self, indices=(0,), period=0.02):
         super().__init__(daemon=True)
-        self.index, self.period = index, period
+        self.indices, self.period = list(indices), period
         self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.in_region = 0
+        self.region = False
         self._halt = threading.Event()
         self.ok = False
         try:
             import pynvml
             pynvml.nvmlInit()
             self.nv = pynvml
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
-            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.h = [pynvml.nvmlDeviceGetHandleByIndex(i) for i in self.indices]
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h[0], pynvml.NVML_CLOCK_SM)
             self.ok = True
         except Exception:
             self.nv = None
@@ -83,23 +91,43 @@ class ClockSampler(threading.Thread):
             getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
         }
         while not self._halt.is_set():
+            for h in self.h:
+                try:
+                    self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                    if self.region:
+                        self.in_region += 1
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    for bit, name in names.items():
+                        if r & bit:
+                            self.reasons.add(name)
+                except Exception:
+                    pass
+            self._halt.wait(self.period)
+
+    def sample_once(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        for h in self.h:
             try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for bit, name in names.items():
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"),
+                                  (0x4, "sw_power_cap"), (0x80, "hw_power_brake")):
                     if r & bit:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._halt.wait(self.period)
 
     def stop(self):
         self._halt.set()
         if self.is_alive():
             self.join(timeout=2)
         s = sorted(self.samples)
-        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(s)}
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_min_mhz": (s[0] if s else None),
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s),
+                "samples_in_timed_region": self.in_region, "gpus": self.indices,
+                "window": "timed region + per-class pass + end-to-end passes (GPUs busy throughout)"}
 
 
 def build_objects(rt, scene):
@@ -211,6 +239,8 @@ def main():
         run_reference(args)
         return
 
+    import ctypes as C
+
     import numpy as np
     import torch
 
@@ -252,9 +282,24 @@ def main():
         sr.redraw(cam, **opts_kw)
     # the sequence path too (its streams and one workspace per pass in flight are created on first use)
     sr.redraw_sequence([cam] * max(args.warmup, (fif + 1) * G), frames_in_flight=fif, **opts_kw)
+    sr.redraw_sequence([cam] * args.steps, frames_in_flight=fif, **opts_kw)      # and once in the timed shape
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    mode = os.environ.get("RTB_BENCH_SAMPLER", "device")     # device (default) | rank0 | all (NVML inside the region) | off
+    sampler = None
+    if mode == "all" or (mode in ("rank0", "device") and rank == 0):
+        sampler = ClockSampler([local_rank] if mode == "all" else list(range(world)))
+        if mode == "device":
+            sampler.sample_once()                               # one NVML reading just before the region
+            barrier()
+        else:
+            sampler.start()
+            sampler.region = True
+    elif mode == "device":
+        barrier()
+    n_sm = rt.device_info()["sm_count"]
+    probe = torch.zeros((2, 2 * n_sm), dtype=torch.int64, device="cuda")
+    pstream = A.stream_arg(torch.cuda.current_stream().cuda_stream)
+    A.check(A.load().rtb_clock_probe(C.c_void_p(probe[0].data_ptr()), n_sm, pstream))
     st_acc = {"p": 0.0, "s": 0.0, "sh": 0.0, "c": 0.0, "k": 0.0, "launches": 0, "nodes": 0, "shadow": 0}
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -263,9 +308,21 @@ def main():
     # fully assembled on every rank inside the region.
     repeats = sr.redraw_sequence([cam] * args.steps, frames_in_flight=fif, **opts_kw)   # no instrumentation inside
     ev1.record()
+    A.check(A.load().rtb_clock_probe(C.c_void_p(probe[1].data_ptr()), n_sm, pstream))
     barrier()
     ms_total = ev0.elapsed_time(ev1)
-    clocks = sampler.stop()
+    if sampler:
+        sampler.region = False
+        if mode == "device":
+            sampler.start()                                     # from here on: per-class pass + end-to-end passes
+    # SM clock of the timed region, measured on the device: cycles / ns per SM between the two probes
+    pr = probe.cpu().numpy().reshape(2, n_sm, 2)
+    okm = (pr[0, :, 1] > 0) & (pr[1, :, 1] > pr[0, :, 1])
+    dev_mhz = float(np.median((pr[1, okm, 0] - pr[0, okm, 0]) / (pr[1, okm, 1] - pr[0, okm, 1]) * 1e3)) if okm.any() else 0.0
+    tm = torch.tensor([dev_mhz if dev_mhz > 0 else 1e9], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(tm, op=dist.ReduceOp.MIN)
+    dev_mhz_min = float(tm.item())
     t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -292,7 +349,6 @@ def main():
     host = torch.empty((H, W, 4), dtype=torch.uint8).pin_memory()
     e2e_launches = 0
 
-    import ctypes as C
     lib = A.load()
     desc = renderer.desc                    # the scene description in HOST memory, marshalled once
     cam_c = cam.to_c()
@@ -379,6 +435,14 @@ def main():
     e2e_ms, single_ms = float(te[0].item()), float(te[1].item())
     e2e_value = rays_per_frame / (e2e_ms * 1e-3) / 1e6
 
+    clocks = sampler.stop() if sampler else {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+    if mode == "device" and dev_mhz_min < 1e8:
+        clocks["nvml_sm_mhz"] = clocks.get("sm_mhz")
+        clocks["sm_mhz"] = round(dev_mhz_min, 1)
+        clocks["how"] = ("sm_mhz: SM cycles / ns between two device probes bracketing the timed region (median over SMs, "
+                         "MIN over ranks); reasons / nvml_sm_mhz: NVML on rank 0, one sample right before the region and "
+                         "every 20 ms during the phases right after it (per-class pass, end-to-end passes) - NVML polling "
+                         "inside a multi-GPU timed region stalls the peer exchange")
     sr.close()                               # collective: unmap the peers' buffers, free this rank's
     if rank != 0:
         renderer.close()

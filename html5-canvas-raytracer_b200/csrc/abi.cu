@@ -366,6 +366,20 @@ int copy_rows_to_host(const RowMap& rm, const uint8_t* d_frame, uint8_t* h_out, 
   return RTB_OK;
 }
 
+// One (clock64, globaltimer) pair per SM: two probes bracket a region, cycles / ns = the SM clock the region
+// actually ran at - measured on the device, without asking the driver (NVML polling during a multi-GPU
+// sequence stalls the exchange for milliseconds).
+__global__ void clock_probe_kernel(unsigned long long* out, int max_sms) {
+  if (threadIdx.x != 0) return;
+  unsigned smid;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+  if ((int)smid >= max_sms) return;
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  out[2 * smid] = (unsigned long long)clock64();
+  out[2 * smid + 1] = t;
+}
+
 __global__ void unstripe_kernel(const uint32_t* __restrict__ gathered, uint32_t* __restrict__ frame, int W,
                                 int H, int S, int world, int padded_rows) {
   // gathered: [rank][padded_rows][W]; local row l of rank r is frame row (l / S) * S * world + r * S + l % S
@@ -610,6 +624,7 @@ int rtb_set_frames_in_flight(int n) {
   if (rc != RTB_OK) return rc;
   g_rtb.frames_in_flight = n;
   g_rtb.next_slot = 0;
+  g_rtb.half_slot = -1;
   return RTB_OK;
 }
 
@@ -768,9 +783,10 @@ int rtb_render_batch(rtb_scene_t s, const RtbCamera* cams, int32_t nframes, cons
   if ((rc = rtb_finish_pending(-1)) != RTB_OK) return rc;
   g_rtb.frames_in_flight = D;
   g_rtb.next_slot = 0;
+  g_rtb.half_slot = -1;
   struct Restore {
     int v;
-    ~Restore() { (void)rtb_finish_pending(-1); g_rtb.frames_in_flight = v; g_rtb.next_slot = 0; }
+    ~Restore() { (void)rtb_finish_pending(-1); g_rtb.frames_in_flight = v; g_rtb.next_slot = 0; g_rtb.half_slot = -1; }
   } restore{saved_in_flight};
   for (int i = 0; i < D; i++) {
     if (!g_rtb.batch_stream[i]) RTB_CUDA(cudaStreamCreateWithFlags(&g_rtb.batch_stream[i], cudaStreamNonBlocking));
@@ -861,6 +877,16 @@ void rtb_default_opts(RtbRenderOpts* o) {
 const char* rtb_last_error(void) { return t_err; }
 const char* rtb_version(void) { return "rtb200 abi 1 sm_100a"; }
 uint32_t rtb_abi_version(void) { return RTB_ABI_VERSION; }
+
+int rtb_clock_probe(uint64_t* d_out, int32_t max_sms, void* cuda_stream) {
+  RTB_API_LOCK();
+  if (!g_rtb.inited) { rtb_set_error("rtb_init() has not been called"); return RTB_ERR_NOT_INIT; }
+  if (!d_out || max_sms < 1) { rtb_set_error("bad clock probe arguments"); return RTB_ERR_INVALID; }
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : g_rtb.stream;
+  clock_probe_kernel<<<g_rtb.sm_count * 4, 32, 0, st>>>(reinterpret_cast<unsigned long long*>(d_out), max_sms);
+  RTB_CUDA(cudaGetLastError());
+  return RTB_OK;
+}
 
 int rtb_device_info(int32_t* sm_count, int32_t* clock_khz, char* name_buf, int32_t name_len) {
   if (!g_rtb.inited) { rtb_set_error("rtb_init() has not been called"); return RTB_ERR_NOT_INIT; }

@@ -86,6 +86,7 @@ struct WfSlot {
   size_t wf_bytes = 0;
   cudaStream_t stream2 = nullptr;             // overlapped early shadow pass
   cudaEvent_t ev_primary = nullptr, ev_early = nullptr, ev_async = nullptr;
+  cudaEvent_t ev_half = nullptr;              // recorded after the last trace level: the next pass in flight may start
   void* h_sticky = nullptr;                   // pinned: overflow flag + device counters of the last call
   // per-camera-origin primary tables of the slot's frame group (packed + exact, RTB_MAX_GROUP sets), their
   // pinned staging, and what each set currently holds (scene uid, padded size, origin)
@@ -117,6 +118,7 @@ struct RtbGlobal {
   WfSlot slot[RTB_MAX_IN_FLIGHT];
   int frames_in_flight = 1;                   // 1 .. RTB_MAX_IN_FLIGHT (rtb_set_frames_in_flight)
   int next_slot = 0, last_slot = 0;
+  int half_slot = -1;                         // slot of the asynchronous pass enqueued last (its ev_half), -1: none
   unsigned long long* d_counters = nullptr;   // 3 x u64 for the pixel kernels
   uint32_t* d_peer_counter = nullptr;         // last-block election words of rtb_peer_scatter
   char* cached_arena = nullptr;               // last destroyed scene's device arena, reused by the next create

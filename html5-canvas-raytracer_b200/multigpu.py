@@ -333,14 +333,25 @@ class StripedRenderer:
         self.flags_host[slot][:self.world].copy_(self._ctl[s0:s0 + self.world], non_blocking=True)
         self.flags_host[slot][self.world:].copy_(self._ctl[_CTL_TIMEOUT:_CTL_TIMEOUT + 1], non_blocking=True)
 
-    def _enqueue_group(self, cams, slot, kw, stats=None):
+    def _mark(self, tr, name):
+        """Tracing (tools/seq_trace.py): a timed CUDA event on the current stream + the host clock."""
+        if tr is not None:
+            import time
+            import torch
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            tr[name] = (ev, time.perf_counter())
+
+    def _enqueue_group(self, cams, slot, kw, stats=None, tr=None):
         """Render + exchange of one group of frames into self.frames[slot][0..n); status words to the host."""
         n = len(cams)
         if n > self.G:
             raise ValueError(f"group of {n} frames exceeds this renderer's group size {self.G}")
+        self._mark(tr, "begin")
         if self.exchange == "p2p":
             self._enqueue_release(slot)
         self._enqueue_render(cams, slot, stats, kw)
+        self._mark(tr, "rendered")
         if self.exchange == "p2p":
             self._enqueue_scatter(slot, n)
         elif self.exchange == "nccl":
@@ -383,7 +394,7 @@ class StripedRenderer:
         raise self._overflow_error()
 
     # -- a sequence of frames (throughput mode) ----------------------------------------------------------
-    def redraw_sequence(self, cameras, on_frame=None, frames_in_flight: int = 0, group: int = 0, **kw):
+    def redraw_sequence(self, cameras, on_frame=None, frames_in_flight: int = 0, group: int = 0, trace=None, **kw):
         """Software-pipelined: the sequence is cut into groups of up to `group` frames (0 = this renderer's group
         size; one wavefront pass each) and up to `frames_in_flight` passes (0 = default_in_flight(world)) are
         enqueued before the host waits for the oldest one, each on its own stream with its own library workspace.
@@ -413,13 +424,21 @@ class StripedRenderer:
                 while i < n and len(inflight) < depth:
                     slot = i % depth
                     with torch.cuda.stream(self._streams[slot]):
-                        self._enqueue_group(cameras[starts[i]:starts[i] + sizes[i]], slot, kw)
+                        tr = None
+                        if trace is not None:
+                            tr = {"group": i, "frames": sizes[i]}
+                            trace.append(tr)
+                        self._enqueue_group(cameras[starts[i]:starts[i] + sizes[i]], slot, kw, tr=tr)
+                        self._mark(tr, "done")
                         done[slot].record()
                     inflight.append(i)
                     i += 1
                 j = inflight.pop(0)
                 jslot = j % depth
                 done[jslot].synchronize()                 # the host waits for group j only
+                if trace is not None:
+                    import time
+                    trace[j]["host_done"] = time.perf_counter()
                 if not self._frame_ok(jslot):             # same words on every rank: same decision everywhere
                     repeats += 1
                     if repeats > MAX_REPEATS:

@@ -303,6 +303,12 @@ uint32_t rtb_abi_version(void);
 /* Device properties the bench needs without importing anything else: SM count, clock (kHz). */
 int rtb_device_info(int32_t* sm_count, int32_t* clock_khz, char* name_buf, int32_t name_len);
 
+/* Diagnostics: enqueue a probe that stores, for every SM that runs one of its blocks, the SM's cycle counter
+ * and the global nanosecond timer into d_out[2*sm], d_out[2*sm + 1] (device memory, 2*max_sms u64, zero it
+ * first).  Two probes around a region give the SM clock the region ran at (delta cycles / delta ns) without
+ * any driver query inside the region. */
+int rtb_clock_probe(uint64_t* d_out, int32_t max_sms, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,6 +12,11 @@ objs = rt.scenes.synth_objects(1024, 1024)
 W, H = 3840, 2160
 cam = rt.scenes.demo_camera(W, H)
 rows = (H + world - 1) // world
+sampler = None
+if os.environ.get("PROBE_SAMPLER"):                      # does the NVML clock sampler of bench.py disturb the enqueue thread?
+    import bench
+    sampler = bench.ClockSampler(0, period=float(os.environ["PROBE_SAMPLER"]))
+    sampler.start()
 with rt.Renderer(objs) as r:
     dev = torch.empty((4, 8, rows, W, 4), dtype=torch.uint8, device="cuda")
     streams = [torch.cuda.Stream() for _ in range(4)]
@@ -38,3 +43,5 @@ with rt.Renderer(objs) as r:
         print(f"world {world}: {N} frames, groups of {G} ({len(sizes)} passes), {D} in flight: {dt:.3f} ms/frame "
               f"(ideal {8.9 / world:.3f}), host enqueue {host:.3f} ms/frame ok={ok}", flush=True)
     r.set_frames_in_flight(1)
+if sampler:
+    print("sampler:", sampler.stop())

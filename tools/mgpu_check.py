@@ -43,13 +43,13 @@ with rt.Renderer(objs, device=local_rank) as r:
                 print(f"rank {rank}:   frame {i}: {len(bad)} px differ, {len(rows)} rows, owner ranks {owners}, equals ref of frame {same_as}", flush=True)
     ok &= all(seq_ok) and rep == 0
     # force an overflow on the LAST rank only: the verdict travels in the gather payload
-    if rank == world - 1:
-        os.environ["RTB_WF_CAP_NODES"] = str(W * 6)
+    if rank == world - 1:                                  # bands sized for 1.1 nodes per ray: the first attempt overflows,
+        os.environ["RTB_WF_CAP_NODES"] = str(W * 9 * mg.default_group(world))   # halved bands (2.2, 4.4 ...) fit
+        os.environ["RTB_WF_NODES_PER_RAY"] = "1.1"
     with rt.Renderer(demo, device=local_rank) as rd:       # demo scene: glass/mirror rows overflow tiny queues
-        saved = os.environ.pop("RTB_WF_CAP_NODES", None)
+        saved = {k: os.environ.pop(k, None) for k in ("RTB_WF_CAP_NODES", "RTB_WF_NODES_PER_RAY")}
         drefs = [rd.redraw(c, **kw) for c in cams]
-        if saved:
-            os.environ["RTB_WF_CAP_NODES"] = saved
+        os.environ.update({k: v for k, v in saved.items() if v})
     with rt.Renderer(demo, device=local_rank) as r2:
         sr2 = mg.StripedRenderer(r2, W, H, rank, world, exchange=XCH)
         f = sr2.redraw(cams[1], **kw).cpu().numpy()
@@ -68,6 +68,7 @@ with rt.Renderer(objs, device=local_rank) as r:
         ok &= all(s3) and rep2 > 0
         sr3.close()
     os.environ.pop("RTB_WF_CAP_NODES", None)
+    os.environ.pop("RTB_WF_NODES_PER_RAY", None)
     sr.close()
     t = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
