@@ -226,7 +226,7 @@ int render_group_to_device(RtbScene_* s, const RtbCamera* cams, int n_frames, co
   if (kernel == RTB_KERNEL_AUTO)
     kernel = (o->precision == RTB_PRECISION_FP64 || s->n_spheres <= RTB_AUTO_PIXEL_MAX_SPHERES ||
               o->star_mode == RTB_STARS_STREAM ||
-              (size_t)s->n_pad * sizeof(float4) > g_rtb.smem_optin)   // tables must fit shared memory
+              2 * (size_t)s->n_pad * sizeof(float4) > g_rtb.smem_optin)   // tables must fit shared memory
                  ? RTB_KERNEL_PIXEL : RTB_KERNEL_WAVEFRONT;
   uint32_t launches = 0;
   if (kernel == RTB_KERNEL_WAVEFRONT) {

@@ -92,6 +92,12 @@ constexpr int WF_THREADS = 256;
 #ifndef WF_MIN_CTAS
 #define WF_MIN_CTAS 2
 #endif
+#ifndef WF_MIN_CTAS_SHADOW
+#define WF_MIN_CTAS_SHADOW 2
+#endif
+#ifndef WF_MIN_CTAS_GENERAL
+#define WF_MIN_CTAS_GENERAL 3            // general rays: 4 per lane fit 80 registers (measured 3.93 -> 3.66 ms per 4K frame)
+#endif
 constexpr float WF_INF = __builtin_huge_valf();
 constexpr int WF_GROUP = 8;              // spheres per candidate check; the unrolled body (4 sphere pairs x R
                                          // rays) must stay well inside the ~6 KB L0 instruction cache
@@ -177,7 +183,7 @@ __device__ __noinline__ unsigned long long slow_primary(const float4* __restrict
     const int b = 31 - __clz((int)m);
     m ^= 1u << b;
     const int jj = j + (8 - 1) - b;
-    const float4 x = __ldg(exact + jj);
+    const float4 x = exact[jj];
     const float tca = -(ndx * x.x + ndy * x.y + ndz * x.z);
     exact_update(tca, tca * tca - x.w, eps, jj, best);
   }
@@ -196,7 +202,7 @@ __device__ __noinline__ unsigned long long slow_general(const float4* __restrict
     const int b = 31 - __clz((int)m);
     m ^= 1u << b;
     const int jj = j + (8 - 1) - b;
-    const float4 s = __ldg(geom + jj);
+    const float4 s = geom[jj];
     const float L0 = s.x + nox, L1 = s.y + noy, L2 = s.z + noz;
     const float tca = dx * L0 + dy * L1 + dz * L2;
     if (jj == self) {
@@ -226,7 +232,7 @@ __device__ __noinline__ float slow_shadow(const float4* __restrict__ exact, cons
     m ^= 1u << b;
     const int jj = j + (8 - 1) - b;
     if (jj == hit_i) continue;                              // main.js:294 — no shadow on self
-    const float4 x = __ldg(exact + jj);
+    const float4 x = exact[jj];
     const float tca = -(nwx * x.x + nwy * x.y + nwz * x.z);
     const float disc = tca * tca - x.w;
     if (disc >= 0.f) {
@@ -622,7 +628,7 @@ RTB_DEVINL void trace_chunks(const WfParams& P, uint32_t* work, uint32_t first, 
       }
     }
     if (PRIMARY) sweep_primary<R>(tab, exact, 0, n_pad, a, active, best, eps);
-    else sweep_general<R>(tab, P.geom, P.b.ray_o, P.b.ray_d, 0, n_pad, a, b, nku, nkv, nodes, self, active, best, eps);
+    else sweep_general<R>(tab, exact, P.b.ray_o, P.b.ray_d, 0, n_pad, a, b, nku, nkv, nodes, self, active, best, eps);
     __syncwarp();
 #pragma unroll
     for (int q = 0; q < R; q++)
@@ -644,17 +650,24 @@ RTB_DEVINL void trace_range(const WfParams& P, float4* tab, const float4* __rest
   // a CTA whose claim lies beyond the range has nothing to do: leave at once (the slot goes to the
   // kernels of the other frames in flight) without even loading the table
   if ((uint64_t)begin + (uint64_t)(first - (threadIdx.x >> 5)) * (32u * (uint32_t)r) < split || split < end) {
-    for (int i = threadIdx.x; i < n_pad; i += blockDim.x) tab[i] = src[i];
+    // both tables in shared memory: the packed sweep table and the exact one the slow path reads
+    // (general rays: the spheres themselves, n entries; the padding is never a candidate)
+    float4* xt = tab + n_pad;
+    const int n_x = PRIMARY ? n_pad : P.sc.n_spheres;
+    for (int i = threadIdx.x; i < n_pad; i += blockDim.x) {
+      tab[i] = src[i];
+      xt[i] = i < n_x ? exact[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     __syncthreads();
-    if (r == RB) trace_chunks<PRIMARY, RB>(P, wa, first, tab, exact, begin, split, lane, my_nodes);
-    else if (r == RB / 2) trace_chunks<PRIMARY, RB / 2>(P, wa, first, tab, exact, begin, split, lane, my_nodes);
-    else trace_chunks<PRIMARY, RB / 4>(P, wa, first, tab, exact, begin, split, lane, my_nodes);
-    if (split < end) trace_chunks<PRIMARY, RB / 4>(P, wt, next_chunk(wt, lane), tab, exact, split, end, lane, my_nodes);
+    if (r == RB) trace_chunks<PRIMARY, RB>(P, wa, first, tab, xt, begin, split, lane, my_nodes);
+    else if (r == RB / 2) trace_chunks<PRIMARY, RB / 2>(P, wa, first, tab, xt, begin, split, lane, my_nodes);
+    else trace_chunks<PRIMARY, RB / 4>(P, wa, first, tab, xt, begin, split, lane, my_nodes);
+    if (split < end) trace_chunks<PRIMARY, RB / 4>(P, wt, next_chunk(wt, lane), tab, xt, split, end, lane, my_nodes);
   }
 }
 
 template <bool PRIMARY>
-__global__ void __launch_bounds__(WF_THREADS, WF_MIN_CTAS)
+__global__ void __launch_bounds__(WF_THREADS, PRIMARY ? WF_MIN_CTAS : WF_MIN_CTAS_GENERAL)
 wf_trace_kernel(const __grid_constant__ WfParams P, int level) {
   extern __shared__ float4 tab[];
   const int n = P.sc.n_spheres;
@@ -672,7 +685,7 @@ wf_trace_kernel(const __grid_constant__ WfParams P, int level) {
   } else {
     uint32_t begin, end;
     level_range(P, level, begin, end);
-    trace_range<false>(P, tab, P.geom_tab, nullptr, begin, end, &P.b.ctr->work_trace[level],
+    trace_range<false>(P, tab, P.geom_tab, P.geom, begin, end, &P.b.ctr->work_trace[level],
                        &P.b.ctr->work_trace_tail[level], lane, my_nodes);
   }
   // stats
@@ -693,7 +706,7 @@ RTB_DEVINL void shadow_chunks(const WfParams& P, int k, const float4* __restrict
                               uint32_t count, uint32_t* work, uint32_t first_chunk, uint32_t lane,
                               unsigned long long& my_rays, unsigned long long& my_tests) {
   const int n = P.sc.n_spheres, n_pad = P.n_pad;
-  const float4* __restrict__ exact = P.light_x[k];
+  const float4* __restrict__ exact = tab + n_pad;          // light_x[k], staged behind the packed table
   const float eps = P.sc.eps;
   const float lx = P.sc.lights[k][0], ly = P.sc.lights[k][1], lz = P.sc.lights[k][2];
   constexpr uint32_t CHUNK = 32u * R;
@@ -794,7 +807,7 @@ RTB_DEVINL void shadow_chunks(const WfParams& P, int k, const float4* __restrict
   }
 }
 
-__global__ void __launch_bounds__(WF_THREADS, WF_MIN_CTAS)
+__global__ void __launch_bounds__(WF_THREADS, WF_MIN_CTAS_SHADOW)
 // phase 0: everything queued for light k.  phase 1 (k = 0 only): the EARLY pass over the entries the
 // primary trace queued ([0, sq_snap0)), launched on a second stream so that it overlaps the secondary
 // trace levels and fills their tails.  phase 2 (k = 0): the rest, [sq_snap0, end).
@@ -812,7 +825,7 @@ wf_shadow_kernel(const __grid_constant__ WfParams P, int k, int phase) {
   const uint32_t split = P.fixed_r ? count : count - tail_rays(count - first, r, R_SHARED / 4);
   const uint32_t fc = cta_claim(work);
   if ((uint64_t)first + (uint64_t)(fc - (threadIdx.x >> 5)) * (32u * (uint32_t)r) < split || split < count) {
-    for (int i = threadIdx.x; i < n_pad; i += blockDim.x) tab[i] = P.light_tab[k][i];
+    for (int i = threadIdx.x; i < n_pad; i += blockDim.x) { tab[i] = P.light_tab[k][i]; tab[n_pad + i] = P.light_x[k][i]; }
     __syncthreads();
     if (r == R_SHARED) shadow_chunks<R_SHARED>(P, k, tab, first, split, work, fc, lane, my_rays, my_tests);
     else if (r == R_SHARED / 2) shadow_chunks<R_SHARED / 2>(P, k, tab, first, split, work, fc, lane, my_rays, my_tests);
@@ -1015,7 +1028,8 @@ int wf_render(RtbScene_* s, const RtbCamera* cams, int n_frames, const DevFrameT
   if (n_frames > RTB_MAX_GROUP) { rtb_set_error("a frame group holds at most %d frames", RTB_MAX_GROUP); return RTB_ERR_INVALID; }
   const int n = s->n_spheres;
   const int n_pad = s->n_pad;
-  const size_t smem = (size_t)n_pad * sizeof(float4);
+  const size_t tab_bytes = (size_t)n_pad * sizeof(float4);
+  const size_t smem = 2 * tab_bytes;                       // packed sweep table + exact table of the slow path
   if (smem > g_rtb.smem_optin) {
     rtb_set_error("wavefront kernels stage all %d spheres in shared memory (%zu B > %zu B available)",
                   n, smem, g_rtb.smem_optin);
@@ -1034,7 +1048,7 @@ int wf_render(RtbScene_* s, const RtbCamera* cams, int n_frames, const DevFrameT
   // staging belong to the workspace slot: the slot's previous pass has been collected before it is reused,
   // so neither is still being read and no host wait is needed here.  Cached per (scene, origin).
   {
-    const size_t need = (size_t)RTB_MAX_GROUP * 2 * smem;
+    const size_t need = (size_t)RTB_MAX_GROUP * 2 * tab_bytes;
     if (sl.ptab_bytes < need) {
       if (sl.d_ptab) { RTB_CUDA(cudaDeviceSynchronize()); cudaFree(sl.d_ptab); cudaFreeHost(sl.h_tab); }
       sl.d_ptab = nullptr; sl.h_tab = nullptr; sl.ptab_bytes = 0;
@@ -1050,13 +1064,13 @@ int wf_render(RtbScene_* s, const RtbCamera* cams, int n_frames, const DevFrameT
       if (f > 0 && o[0] == cams[f - 1].origin[0] && o[1] == cams[f - 1].origin[1] && o[2] == cams[f - 1].origin[2]) continue;
       const int g = n_runs++;
       P.run_begin[g] = f;
-      float4* d_tab = reinterpret_cast<float4*>(sl.d_ptab + (size_t)g * 2 * smem);
+      float4* d_tab = reinterpret_cast<float4*>(sl.d_ptab + (size_t)g * 2 * tab_bytes);
       float4* d_x = d_tab + n_pad;
       if (sl.tab_scene[g] != s->uid || sl.tab_n_pad[g] != n_pad || sl.tab_origin[g][0] != o[0] ||
           sl.tab_origin[g][1] != o[1] || sl.tab_origin[g][2] != o[2]) {
-        float4* h_tab = reinterpret_cast<float4*>(sl.h_tab + (size_t)g * 2 * smem);
+        float4* h_tab = reinterpret_cast<float4*>(sl.h_tab + (size_t)g * 2 * tab_bytes);
         wf_make_table(s->spheres.data(), n, n_pad, o, h_tab, h_tab + n_pad);
-        RTB_CUDA(cudaMemcpyAsync(d_tab, h_tab, 2 * smem, cudaMemcpyHostToDevice, st));
+        RTB_CUDA(cudaMemcpyAsync(d_tab, h_tab, 2 * tab_bytes, cudaMemcpyHostToDevice, st));
         uploaded = true;
         sl.tab_scene[g] = s->uid; sl.tab_n_pad[g] = n_pad;
         for (int c = 0; c < 3; c++) sl.tab_origin[g][c] = o[c];
