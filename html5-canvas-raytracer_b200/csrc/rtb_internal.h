@@ -33,8 +33,8 @@ struct WfCounters {          // one small device struct, zeroed per band
 struct WfBuffers {
   uint32_t cap_nodes;
   float4* ray_o;   // ox, oy, oz, dx                        (levels >= 2)
-  float4* ray_d;   // dy, dz, weight (albedo[3|4] of parent), unused
-  int2* link;      // parent node, meta = path code | segs_left << 24
+  float4* ray_d;   // dy, dz, weight (albedo[3|4] of parent), sphere the ray starts on (hit_i of the parent, int bits)
+  int4* link;      // parent node, meta = path code | segs_left << 24, level-1 ancestor (frame, pixel, sub-sample), unused
   float4* pos;     // hit.p.xyz, hit_i (int bits); hit_i < 0: no hit (main.js:231)
   float4* base;    // sampler rgb, facing-light mask (int bits)
   float4* lq;      // q0, s0, q1, s1   (q = shadow_dot / light_mag, s = pow(spec_dot, se))
@@ -42,7 +42,12 @@ struct WfBuffers {
   float4* acc;     // light_intensity carry, diffuse sum, specular sum, unused
   float4* child_a; // reflect_color (already scaled by albedo[3]) written by the child's compose
   float4* child_b; // refract_color (scaled by albedo[4])
-  uint32_t* sq[RTB_MAX_LIGHTS];   // shadow queues: node indices waiting for light k's occluder sweep
+  uint32_t* sq[RTB_MAX_LIGHTS];   // shadow queues: node indices waiting for light k's occluder sweep (fused pipeline);
+                                  // split pipeline: surviving light_intensity of queue entry e (float bits)
+  // split pipeline only (sweep kernels + hit / post kernels):
+  unsigned long long* key;        // closest hit of the node's ray: (t bits, sphere index, flip) or KEY_NONE
+  float4* srec_a[RTB_MAX_LIGHTS]; // shadow ray records per light: nw.xyz (= -(direction light -> p)), light_len
+  int4* srec_b[RTB_MAX_LIGHTS];   //   node, sphere the ray leaves (hit_i), light_intensity carried so far (float bits), unused
   WfCounters* ctr;
 };
 

@@ -95,6 +95,15 @@ constexpr int WF_THREADS = 256;
 #ifndef WF_MIN_CTAS_SHADOW
 #define WF_MIN_CTAS_SHADOW 2
 #endif
+#ifndef RTB_WF_SPLIT_DEFAULT
+#define RTB_WF_SPLIT_DEFAULT 0
+#endif
+#ifndef WF_MIN_CTAS_SWEEP_PRIMARY
+#define WF_MIN_CTAS_SWEEP_PRIMARY 2
+#endif
+#ifndef WF_MIN_CTAS_HIT
+#define WF_MIN_CTAS_HIT 3
+#endif
 #ifndef WF_MIN_CTAS_GENERAL
 #define WF_MIN_CTAS_GENERAL 3            // general rays: 4 per lane fit 80 registers (measured 3.93 -> 3.66 ms per 4K frame)
 #endif
@@ -340,7 +349,65 @@ struct WfRay {
 // compose: hit record (main.js:441-447), reflect / refract directions (233-266), sampler (320), the
 // occlusion-independent light terms (286-292, 306-313); then warp-compacted queue pushes.
 // Must be called by all 32 lanes together (ballots inside).
-__device__ __noinline__ void process_hit(const WfParams& P, const WfRay& r, unsigned long long key, uint32_t lane) {
+// Shadow ray of light k toward p as the occluder sweep wants it: a = (nw, light_len), nw = -(direction
+// light -> p) (main.js:287-290; the sweep runs from the light).
+RTB_DEVINL float4 shadow_record(const WfParams& P, int k, float px, float py, float pz) {
+  float wx = px - P.sc.lights[k][0], wy = py - P.sc.lights[k][1], wz = pz - P.sc.lights[k][2];
+  const float len = sqrtf(wx * wx + wy * wy + wz * wz);
+  if (len != 0.f) { const float rr = 1.f / len; wx *= rr; wy *= rr; wz *= rr; }
+  return make_float4(-wx, -wy, -wz, len);
+}
+
+// Queue space for a warp's pushes: counts[0] = child nodes, counts[1 + k] = entries of shadow queue k; on
+// return counts[] holds the warp's first index in each queue.
+// AGG = false (fused persistent kernels: warps run independently): one atomic per warp and counter.
+// AGG = true (hit / post kernels: the warps of a CTA walk the same 256-node tile together): the counts of the
+// CTA's warps are summed in shared memory and ONE atomic per counter reserves space for the whole tile - the
+// level counters are single addresses, and with one atomic per warp a kernel that does nothing but hit
+// processing runs at the L2's same-address atomic rate (measured: 8.3 M nodes in 532 us, 252 us per tile).
+// Contains CTA barriers when AGG.
+template <bool AGG>
+RTB_DEVINL void reserve(const WfParams& P, uint32_t (&counts)[1 + RTB_MAX_LIGHTS], int n_lights, int first_light,
+                        uint32_t lane) {
+  if (!AGG) {
+#pragma unroll
+    for (int j = 0; j < 1 + RTB_MAX_LIGHTS; j++) {
+      if (j > n_lights || j < first_light) continue;
+      uint32_t* counter = j == 0 ? &P.b.ctr->node_count : &P.b.ctr->sq_count[j - 1];
+      uint32_t base = 0;
+      if (lane == 0 && counts[j]) base = atomicAdd(counter, counts[j]);
+      counts[j] = __shfl_sync(0xffffffffu, base, 0);
+    }
+    return;
+  }
+  __shared__ uint32_t s_cnt[1 + RTB_MAX_LIGHTS][WF_WARPS];
+  const uint32_t w = threadIdx.x >> 5;
+  if (lane == 0) {
+#pragma unroll
+    for (int j = 0; j < 1 + RTB_MAX_LIGHTS; j++) s_cnt[j][w] = counts[j];
+  }
+  __syncthreads();
+  if ((int)threadIdx.x <= n_lights && (int)threadIdx.x >= first_light) {   // thread j owns counter j
+    const int j = threadIdx.x;
+    uint32_t sum = 0;
+    for (int i = 0; i < WF_WARPS; i++) { const uint32_t c = s_cnt[j][i]; s_cnt[j][i] = sum; sum += c; }
+    uint32_t* counter = j == 0 ? &P.b.ctr->node_count : &P.b.ctr->sq_count[j - 1];
+    const uint32_t base = sum ? atomicAdd(counter, sum) : 0u;
+    for (int i = 0; i < WF_WARPS; i++) s_cnt[j][i] += base;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 1 + RTB_MAX_LIGHTS; j++) counts[j] = s_cnt[j][w];
+  // no third barrier: a warp only ever rewrites its OWN column before the next tile's first barrier, and the
+  // scanning threads touch the other columns only after that barrier, which every reader has then passed
+}
+
+// RECORDS = false: a queued shadow ray is the node index (the fused shadow kernel follows queue -> pos -> acc).
+// RECORDS = true : it is a complete record (direction, length, node, sphere it leaves, light_intensity carried
+//                  so far) that the occluder sweep kernel reads with two coalesced loads.
+// AGG: see reserve().  Must be called by all 32 lanes together (ballots inside), with AGG by the whole CTA.
+template <bool RECORDS, bool AGG>
+RTB_DEVINL void process_hit_impl(const WfParams& P, const WfRay& r, unsigned long long key, uint32_t lane) {
   const bool active = r.active;
   const uint32_t node = r.node;
   const float* o = r.o;
@@ -450,41 +517,54 @@ __device__ __noinline__ void process_hit(const WfParams& P, const WfRay& r, unsi
     }
   }
 
-  // ---- warp-compacted child allocation (north star: ballot/shuffle compaction of live rays) ---------
+  // ---- warp-compacted allocation (north star: ballot/shuffle compaction of live rays): children, and the
+  //      shadow queue of the first light that faces the surface ----------------------------------------------
   const uint32_t b1 = __ballot_sync(0xffffffffu, want_refl);
   const uint32_t b2 = __ballot_sync(0xffffffffu, want_refr);
-  const uint32_t total = __popc(b1) + __popc(b2);
-  if (total) {
-    uint32_t cbase = 0;
-    if (lane == 0) cbase = atomicAdd(&P.b.ctr->node_count, total);
-    cbase = __shfl_sync(0xffffffffu, cbase, 0) + P.n_sub;
-    if (want_refl) {
-      const uint32_t c = cbase + __popc(b1 & lanemask_lt());
-      if (c < P.b.cap_nodes) {
-        P.b.ray_o[c] = make_float4(p[0], p[1], p[2], rdir[0]);
-        P.b.ray_d[c] = make_float4(rdir[1], rdir[2], w_refl, __uint_as_float(r.pixsub));
-        P.b.link[c] = make_int2((int)node, (int)((2u * r.path) | ((uint32_t)(r.segs_left - 1) << 24)));
-      } else { P.b.ctr->overflow = 1u; P.sticky->overflow = 1u; }
-    }
-    if (want_refr) {
-      const uint32_t c = cbase + __popc(b1) + __popc(b2 & lanemask_lt());
-      if (c < P.b.cap_nodes) {
-        P.b.ray_o[c] = make_float4(p[0], p[1], p[2], fdir[0]);
-        P.b.ray_d[c] = make_float4(fdir[1], fdir[2], w_refr, __uint_as_float(r.pixsub));
-        P.b.link[c] = make_int2((int)node, (int)((2u * r.path + 1u) | ((uint32_t)(r.segs_left - 1) << 24)));
-      } else { P.b.ctr->overflow = 1u; P.sticky->overflow = 1u; }
+  uint32_t bk[RTB_MAX_LIGHTS];
+  uint32_t counts[1 + RTB_MAX_LIGHTS];
+  counts[0] = __popc(b1) + __popc(b2);
+#pragma unroll
+  for (int k = 0; k < RTB_MAX_LIGHTS; k++) {
+    bk[k] = k < P.sc.n_lights ? __ballot_sync(0xffffffffu, first_light == k) : 0u;
+    counts[1 + k] = __popc(bk[k]);
+  }
+  reserve<AGG>(P, counts, P.sc.n_lights, 0, lane);
+  const uint32_t cbase = counts[0] + P.n_sub;
+  if (want_refl) {
+    const uint32_t c = cbase + __popc(b1 & lanemask_lt());
+    if (c < P.b.cap_nodes) {
+      P.b.ray_o[c] = make_float4(p[0], p[1], p[2], rdir[0]);
+      P.b.ray_d[c] = make_float4(rdir[1], rdir[2], w_refl, __int_as_float(hit_i));
+      P.b.link[c] = make_int4((int)node, (int)((2u * r.path) | ((uint32_t)(r.segs_left - 1) << 24)), (int)r.pixsub, 0);
+    } else { P.b.ctr->overflow = 1u; P.sticky->overflow = 1u; }
+  }
+  if (want_refr) {
+    const uint32_t c = cbase + __popc(b1) + __popc(b2 & lanemask_lt());
+    if (c < P.b.cap_nodes) {
+      P.b.ray_o[c] = make_float4(p[0], p[1], p[2], fdir[0]);
+      P.b.ray_d[c] = make_float4(fdir[1], fdir[2], w_refr, __int_as_float(hit_i));
+      P.b.link[c] = make_int4((int)node, (int)((2u * r.path + 1u) | ((uint32_t)(r.segs_left - 1) << 24)), (int)r.pixsub, 0);
+    } else { P.b.ctr->overflow = 1u; P.sticky->overflow = 1u; }
+  }
+#pragma unroll
+  for (int k = 0; k < RTB_MAX_LIGHTS; k++) {
+    if (first_light == k) {
+      const uint32_t e = counts[1 + k] + __popc(bk[k] & lanemask_lt());
+      if (RECORDS) {
+        P.b.srec_a[k][e] = shadow_record(P, k, p[0], p[1], p[2]);
+        P.b.srec_b[k][e] = make_int4((int)node, hit_i, __float_as_int(P.sc.light_intensity), 0);
+      } else {
+        P.b.sq[k][e] = node;
+      }
     }
   }
-  // ---- warp-compacted shadow queue push: first light that faces the surface -------------------------
-  for (int k = 0; k < P.sc.n_lights; k++) {
-    const uint32_t bk = __ballot_sync(0xffffffffu, first_light == k);
-    if (!bk) continue;
-    const int leader = __ffs((int)bk) - 1;
-    uint32_t qb = 0;
-    if ((int)lane == leader) qb = atomicAdd(&P.b.ctr->sq_count[k], (uint32_t)__popc(bk));
-    qb = __shfl_sync(0xffffffffu, qb, leader);
-    if (first_light == k) P.b.sq[k][qb + __popc(bk & lanemask_lt())] = node;
-  }
+}
+
+// The fused trace kernels call hit processing out of line (their hot loops must stay small).
+template <bool RECORDS>
+__device__ __noinline__ void process_hit(const WfParams& P, const WfRay& r, unsigned long long key, uint32_t lane) {
+  process_hit_impl<RECORDS, false>(P, r, key, lane);
 }
 
 // ---- RAYGEN ---------------------------------------------------------------------------------------------
@@ -552,7 +632,7 @@ RTB_DEVINL void ray_setup(const WfParams& P, uint32_t node, float (&a)[3], float
     a[0] = -d.x; a[1] = -d.y; a[2] = -d.z;
   } else {
     const float4 ro = P.b.ray_o[node], rd = P.b.ray_d[node];
-    self = __float_as_int(P.b.pos[P.b.link[node].x].w);
+    self = __float_as_int(rd.w);                           // hit_i of the parent node, stored with the ray
     const float dx = ro.w, dy = rd.x, dz = rd.y;
     // branchless orthonormal basis (Duff et al. 2017): u, v unit, u.v = u.d = v.d = 0 to ~1 ulp
     const float sg = copysignf(1.f, dz);
@@ -581,12 +661,12 @@ RTB_DEVINL WfRay ray_record(const WfParams& P, uint32_t node, bool active, float
     r.d[0] = r.d[1] = r.d[2] = 0.f;
     if (active) {
       const float4 ro = P.b.ray_o[node], rd = P.b.ray_d[node];
-      const int2 lk = P.b.link[node];
+      const int4 lk = P.b.link[node];
       r.o[0] = ro.x; r.o[1] = ro.y; r.o[2] = ro.z;
       r.d[0] = ro.w; r.d[1] = rd.x; r.d[2] = rd.y;
       r.path = (uint32_t)lk.y & 0xffffffu;
       r.segs_left = (int)((uint32_t)lk.y >> 24);
-      r.pixsub = __float_as_uint(rd.w);                  // pixel*spp+sub of the level-1 ancestor
+      r.pixsub = (uint32_t)lk.z;                         // level-1 node (frame, pixel, sub-sample) of the ancestor
     }
   }
   return r;
@@ -594,7 +674,7 @@ RTB_DEVINL WfRay ray_record(const WfParams& P, uint32_t node, bool active, float
 
 // `first` is the warp's first chunk, claimed for the whole CTA at once (cta_claim); the following ones
 // are pulled per warp.
-template <bool PRIMARY, int R>
+template <bool PRIMARY, int R, bool SPLIT, bool RECORDS>
 RTB_DEVINL void trace_chunks(const WfParams& P, uint32_t* work, uint32_t first, const float4* __restrict__ tab,
                              const float4* __restrict__ exact, uint32_t begin, uint32_t end, uint32_t lane,
                              unsigned long long& my_nodes) {
@@ -629,16 +709,22 @@ RTB_DEVINL void trace_chunks(const WfParams& P, uint32_t* work, uint32_t first, 
     }
     if (PRIMARY) sweep_primary<R>(tab, exact, 0, n_pad, a, active, best, eps);
     else sweep_general<R>(tab, exact, P.b.ray_o, P.b.ray_d, 0, n_pad, a, b, nku, nkv, nodes, self, active, best, eps);
-    __syncwarp();
+    if (SPLIT) {                                          // the hit kernel takes it from here
 #pragma unroll
-    for (int q = 0; q < R; q++)
-      process_hit(P, ray_record<PRIMARY>(P, nodes[q], active[q], a[q][0], a[q][1], a[q][2]), best[q], lane);
+      for (int q = 0; q < R; q++)
+        if (active[q]) P.b.key[nodes[q]] = best[q];
+    } else {
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < R; q++)
+        process_hit<RECORDS>(P, ray_record<PRIMARY>(P, nodes[q], active[q], a[q][0], a[q][1], a[q][2]), best[q], lane);
+    }
   }
 }
 
 // One contiguous range of rays that share a sweep table: a whole level of general rays, or the primary rays
 // of one run of frames with a common camera origin.  Contains CTA barriers: called by all threads.
-template <bool PRIMARY>
+template <bool PRIMARY, bool SPLIT, bool RECORDS>
 RTB_DEVINL void trace_range(const WfParams& P, float4* tab, const float4* __restrict__ src,
                             const float4* __restrict__ exact, uint32_t begin, uint32_t end, uint32_t* wa,
                             uint32_t* wt, uint32_t lane, unsigned long long& my_nodes) {
@@ -659,16 +745,15 @@ RTB_DEVINL void trace_range(const WfParams& P, float4* tab, const float4* __rest
       xt[i] = i < n_x ? exact[i] : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncthreads();
-    if (r == RB) trace_chunks<PRIMARY, RB>(P, wa, first, tab, xt, begin, split, lane, my_nodes);
-    else if (r == RB / 2) trace_chunks<PRIMARY, RB / 2>(P, wa, first, tab, xt, begin, split, lane, my_nodes);
-    else trace_chunks<PRIMARY, RB / 4>(P, wa, first, tab, xt, begin, split, lane, my_nodes);
-    if (split < end) trace_chunks<PRIMARY, RB / 4>(P, wt, next_chunk(wt, lane), tab, xt, split, end, lane, my_nodes);
+    if (r == RB) trace_chunks<PRIMARY, RB, SPLIT, RECORDS>(P, wa, first, tab, xt, begin, split, lane, my_nodes);
+    else if (r == RB / 2) trace_chunks<PRIMARY, RB / 2, SPLIT, RECORDS>(P, wa, first, tab, xt, begin, split, lane, my_nodes);
+    else trace_chunks<PRIMARY, RB / 4, SPLIT, RECORDS>(P, wa, first, tab, xt, begin, split, lane, my_nodes);
+    if (split < end) trace_chunks<PRIMARY, RB / 4, SPLIT, RECORDS>(P, wt, next_chunk(wt, lane), tab, xt, split, end, lane, my_nodes);
   }
 }
 
-template <bool PRIMARY>
-__global__ void __launch_bounds__(WF_THREADS, PRIMARY ? WF_MIN_CTAS : WF_MIN_CTAS_GENERAL)
-wf_trace_kernel(const __grid_constant__ WfParams P, int level) {
+template <bool PRIMARY, bool SPLIT, bool RECORDS>
+RTB_DEVINL void trace_body(const WfParams& P, int level) {
   extern __shared__ float4 tab[];
   const int n = P.sc.n_spheres;
   const uint32_t lane = threadIdx.x & 31u;
@@ -678,21 +763,63 @@ wf_trace_kernel(const __grid_constant__ WfParams P, int level) {
     // table); a CTA moves on to the next run while others still finish the previous one
     for (int g = 0; g < P.n_runs; g++) {
       if (g > 0) __syncthreads();                          // table and claim word are reused
-      trace_range<true>(P, tab, P.primary_tab[g], P.primary_x[g], (uint32_t)P.run_begin[g] * P.n_sub_frame,
-                        (uint32_t)P.run_begin[g + 1] * P.n_sub_frame, &P.b.ctr->work_primary[g],
-                        &P.b.ctr->work_primary_tail[g], lane, my_nodes);
+      trace_range<true, SPLIT, RECORDS>(P, tab, P.primary_tab[g], P.primary_x[g], (uint32_t)P.run_begin[g] * P.n_sub_frame,
+                               (uint32_t)P.run_begin[g + 1] * P.n_sub_frame, &P.b.ctr->work_primary[g],
+                               &P.b.ctr->work_primary_tail[g], lane, my_nodes);
     }
   } else {
     uint32_t begin, end;
     level_range(P, level, begin, end);
-    trace_range<false>(P, tab, P.geom_tab, P.geom, begin, end, &P.b.ctr->work_trace[level],
-                       &P.b.ctr->work_trace_tail[level], lane, my_nodes);
+    trace_range<false, SPLIT, RECORDS>(P, tab, P.geom_tab, P.geom, begin, end, &P.b.ctr->work_trace[level],
+                              &P.b.ctr->work_trace_tail[level], lane, my_nodes);
   }
   // stats
   for (int o2 = 16; o2 > 0; o2 >>= 1) my_nodes += __shfl_down_sync(0xffffffffu, my_nodes, o2);
   if (lane == 0 && my_nodes) {
     atomicAdd(&P.sticky->nodes, my_nodes);
     atomicAdd(&P.sticky->sphere_tests, my_nodes * (unsigned long long)n);
+  }
+  if (!SPLIT) publish_level(P, level);                    // split pipeline: the hit kernel creates the children
+}
+
+// Fused pipeline: sweep + hit processing of a level in one persistent kernel.
+template <bool PRIMARY, bool RECORDS>
+__global__ void __launch_bounds__(WF_THREADS, PRIMARY ? WF_MIN_CTAS : WF_MIN_CTAS_GENERAL)
+wf_trace_kernel(const __grid_constant__ WfParams P, int level) {
+  trace_body<PRIMARY, false, RECORDS>(P, level);
+}
+
+// Split pipeline, step 1 of a level: the closest-hit SWEEP alone.  key[node] = (t bits, sphere, flip) or
+// KEY_NONE.  Every resident warp is in the FMA-bound sweep nearly all the time; nothing here waits on the
+// scattered loads and stores of hit processing.
+template <bool PRIMARY>
+__global__ void __launch_bounds__(WF_THREADS, PRIMARY ? WF_MIN_CTAS_SWEEP_PRIMARY : WF_MIN_CTAS_GENERAL)
+wf_sweep_kernel(const __grid_constant__ WfParams P, int level) {
+  trace_body<PRIMARY, true, false>(P, level);
+}
+
+// Split pipeline, step 2 of a level: HIT PROCESSING, one thread per ray at high occupancy - the work is
+// scattered loads (material, texels) and stores (node record, child rays, shadow records), i.e. latency
+// bound, and wants many warps, not many registers.  Warps take 32 consecutive nodes at a time, so the
+// ballot-compacted queue pushes see the same neighbours as in the fused kernels.
+template <bool PRIMARY, bool RECORDS>
+__global__ void __launch_bounds__(WF_THREADS, WF_MIN_CTAS_HIT)
+wf_hit_kernel(const __grid_constant__ WfParams P, int level) {
+  uint32_t begin, end;
+  level_range(P, level, begin, end);
+  const uint32_t lane = threadIdx.x & 31u;
+  // the CTA walks tiles of 256 consecutive nodes: queue space is reserved once per tile (reserve<true>)
+  for (uint64_t base = (uint64_t)begin + (uint64_t)blockIdx.x * WF_THREADS; base < end;
+       base += (uint64_t)gridDim.x * WF_THREADS) {
+    const uint32_t node = (uint32_t)base + threadIdx.x;
+    const bool active = node < end;
+    float ndx = 0.f, ndy = 0.f, ndz = 0.f;
+    unsigned long long key = KEY_NONE;
+    if (active) {
+      key = P.b.key[node];
+      if (PRIMARY) { const float4 d = P.b.ray_o[node]; ndx = -d.x; ndy = -d.y; ndz = -d.z; }
+    }
+    process_hit_impl<RECORDS, true>(P, ray_record<PRIMARY>(P, node, active, ndx, ndy, ndz), key, lane);
   }
   publish_level(P, level);
 }
@@ -701,7 +828,7 @@ wf_trace_kernel(const __grid_constant__ WfParams P, int level) {
 // Occluder sweep of main.js:293-304 for light k, traced from the light toward hit.p.  Same fast test as
 // sweep_primary (table = C - light, sc); the slow path applies the reference's [0.001, light_len)
 // window along the reference's own ray (from hit.p toward the light): t = light_len - s.
-template <int R>
+template <int R, bool SPLIT>
 RTB_DEVINL void shadow_chunks(const WfParams& P, int k, const float4* __restrict__ tab, uint32_t first,
                               uint32_t count, uint32_t* work, uint32_t first_chunk, uint32_t lane,
                               unsigned long long& my_rays, unsigned long long& my_tests) {
@@ -725,7 +852,16 @@ RTB_DEVINL void shadow_chunks(const WfParams& P, int k, const float4* __restrict
       active[q] = e < count;
       node[q] = 0; hit_i[q] = -1; len[q] = 0.f; I[q] = 0.f; mask[q] = 0;
       nw[q][0] = nw[q][1] = nw[q][2] = 0.f;                // idle / dead slot: never a candidate
-      if (active[q]) {
+      if (active[q] && SPLIT) {                             // complete ray record, two coalesced loads
+        const float4 ra = P.b.srec_a[k][e];
+        const int4 rb = P.b.srec_b[k][e];
+        node[q] = (uint32_t)rb.x;
+        hit_i[q] = rb.y;
+        len[q] = ra.w;
+        I[q] = __int_as_float(rb.z);
+        my_rays++;
+        if (I[q] != 0.f) { nw[q][0] = ra.x; nw[q][1] = ra.y; nw[q][2] = ra.z; }
+      } else if (active[q]) {
         node[q] = P.b.sq[k][e];
         const float4 ps = P.b.pos[node[q]];
         hit_i[q] = __float_as_int(ps.w);
@@ -775,6 +911,12 @@ RTB_DEVINL void shadow_chunks(const WfParams& P, int k, const float4* __restrict
         }
       }
     }
+    if (SPLIT) {                                            // wf_spost_kernel accumulates and hands on
+#pragma unroll
+      for (int q = 0; q < R; q++)
+        if (active[q]) P.b.sq[k][(uint32_t)base + (uint32_t)q * 32u + lane] = __float_as_uint(I[q]);
+      continue;
+    }
 #pragma unroll
     for (int q = 0; q < R; q++) {
       int next = -1;
@@ -807,17 +949,23 @@ RTB_DEVINL void shadow_chunks(const WfParams& P, int k, const float4* __restrict
   }
 }
 
-__global__ void __launch_bounds__(WF_THREADS, WF_MIN_CTAS_SHADOW)
 // phase 0: everything queued for light k.  phase 1 (k = 0 only): the EARLY pass over the entries the
 // primary trace queued ([0, sq_snap0)), launched on a second stream so that it overlaps the secondary
 // trace levels and fills their tails.  phase 2 (k = 0): the rest, [sq_snap0, end).
-wf_shadow_kernel(const __grid_constant__ WfParams P, int k, int phase) {
+RTB_DEVINL void shadow_range(const WfParams& P, int k, int phase, uint32_t& first, uint32_t& count) {
+  first = 0;
+  count = *((volatile uint32_t*)&P.b.ctr->sq_count[k]);
+  if (phase == 1) count = *((volatile uint32_t*)&P.b.ctr->sq_snap0);
+  else if (phase == 2) first = *((volatile uint32_t*)&P.b.ctr->sq_snap0);
+}
+
+template <bool SPLIT>
+RTB_DEVINL void shadow_body(const WfParams& P, int k, int phase) {
   extern __shared__ float4 tab[];
   const int n_pad = P.n_pad;
-  uint32_t first = 0, count = *((volatile uint32_t*)&P.b.ctr->sq_count[k]);
-  uint32_t* work = &P.b.ctr->work_shadow[k];
-  if (phase == 1) { count = *((volatile uint32_t*)&P.b.ctr->sq_snap0); work = &P.b.ctr->work_shadow_early; }
-  else if (phase == 2) first = *((volatile uint32_t*)&P.b.ctr->sq_snap0);
+  uint32_t first, count;
+  shadow_range(P, k, phase, first, count);
+  uint32_t* work = (phase == 1) ? &P.b.ctr->work_shadow_early : &P.b.ctr->work_shadow[k];
   const uint32_t lane = threadIdx.x & 31u;
   unsigned long long my_rays = 0, my_tests = 0;
   uint32_t* work_tail = (phase == 1) ? &P.b.ctr->work_shadow_early_tail : &P.b.ctr->work_shadow_tail[k];
@@ -827,11 +975,11 @@ wf_shadow_kernel(const __grid_constant__ WfParams P, int k, int phase) {
   if ((uint64_t)first + (uint64_t)(fc - (threadIdx.x >> 5)) * (32u * (uint32_t)r) < split || split < count) {
     for (int i = threadIdx.x; i < n_pad; i += blockDim.x) { tab[i] = P.light_tab[k][i]; tab[n_pad + i] = P.light_x[k][i]; }
     __syncthreads();
-    if (r == R_SHARED) shadow_chunks<R_SHARED>(P, k, tab, first, split, work, fc, lane, my_rays, my_tests);
-    else if (r == R_SHARED / 2) shadow_chunks<R_SHARED / 2>(P, k, tab, first, split, work, fc, lane, my_rays, my_tests);
-    else shadow_chunks<R_SHARED / 4>(P, k, tab, first, split, work, fc, lane, my_rays, my_tests);
+    if (r == R_SHARED) shadow_chunks<R_SHARED, SPLIT>(P, k, tab, first, split, work, fc, lane, my_rays, my_tests);
+    else if (r == R_SHARED / 2) shadow_chunks<R_SHARED / 2, SPLIT>(P, k, tab, first, split, work, fc, lane, my_rays, my_tests);
+    else shadow_chunks<R_SHARED / 4, SPLIT>(P, k, tab, first, split, work, fc, lane, my_rays, my_tests);
     if (split < count)
-      shadow_chunks<R_SHARED / 4>(P, k, tab, split, count, work_tail, next_chunk(work_tail, lane), lane, my_rays, my_tests);
+      shadow_chunks<R_SHARED / 4, SPLIT>(P, k, tab, split, count, work_tail, next_chunk(work_tail, lane), lane, my_rays, my_tests);
   }
   for (int o2 = 16; o2 > 0; o2 >>= 1) {
     my_rays += __shfl_down_sync(0xffffffffu, my_rays, o2);
@@ -840,6 +988,74 @@ wf_shadow_kernel(const __grid_constant__ WfParams P, int k, int phase) {
   if (lane == 0 && my_rays) {
     atomicAdd(&P.sticky->shadow_rays, my_rays);
     atomicAdd(&P.sticky->sphere_tests, my_tests);
+  }
+}
+
+// Fused pipeline: occluder sweep + accumulation + hand-off to the next facing light.
+__global__ void __launch_bounds__(WF_THREADS, WF_MIN_CTAS_SHADOW)
+wf_shadow_kernel(const __grid_constant__ WfParams P, int k, int phase) {
+  shadow_body<false>(P, k, phase);
+}
+
+// Split pipeline: the occluder SWEEP alone, from complete ray records; the surviving light_intensity of
+// entry e goes to sq[k][e] (float bits).
+__global__ void __launch_bounds__(WF_THREADS, WF_MIN_CTAS_SHADOW)
+wf_ssweep_kernel(const __grid_constant__ WfParams P, int k, int phase) {
+  shadow_body<true>(P, k, phase);
+}
+
+// Split pipeline: what follows the sweep of light k for every entry - main.js:305-313 (diffuse / specular
+// sums) and the hand-off of the carried light_intensity to the next light that faces the surface
+// (main.js:284: declared once outside the loop), as a new ray record.  One thread per entry.
+__global__ void __launch_bounds__(WF_THREADS, WF_MIN_CTAS_HIT)
+wf_spost_kernel(const __grid_constant__ WfParams P, int k, int phase) {
+  uint32_t first, count;
+  shadow_range(P, k, phase, first, count);
+  const uint32_t lane = threadIdx.x & 31u;
+  for (uint64_t base = (uint64_t)first + (uint64_t)blockIdx.x * WF_THREADS; base < count;
+       base += (uint64_t)gridDim.x * WF_THREADS) {
+    const uint32_t e = (uint32_t)base + threadIdx.x;
+    int next = -1;
+    uint32_t node = 0;
+    int hit_i = -1;
+    float I = 0.f;
+    if (e < count) {
+      const int4 rb = P.b.srec_b[k][e];
+      node = (uint32_t)rb.x;
+      hit_i = rb.y;
+      I = __uint_as_float(P.b.sq[k][e]);
+      float4 a = P.b.acc[node];
+      a.x = I;
+      const uint32_t lmask = (uint32_t)__float_as_int(P.b.base[node].w) & 0xffu;
+      if (I != 0.f) {                                      // main.js:305-313
+        const float4 lq = (k < 2) ? P.b.lq[node] : P.b.lq2[node];
+        const float qk = (k & 1) ? lq.z : lq.x, sk = (k & 1) ? lq.w : lq.y;
+        a.y += I * qk;
+        a.z += sk;
+      }
+      P.b.acc[node] = a;
+      const uint32_t rest = lmask & ~((2u << k) - 1u);     // facing lights after k
+      if (I != 0.f && rest) next = __ffs((int)rest) - 1;   // carry light_intensity to that light
+    }
+    if (k + 1 >= P.sc.n_lights) continue;                   // last light: nobody to hand on to
+    uint32_t bk[RTB_MAX_LIGHTS];
+    uint32_t counts[1 + RTB_MAX_LIGHTS];
+    counts[0] = 0;
+#pragma unroll
+    for (int k2 = 0; k2 < RTB_MAX_LIGHTS; k2++) {
+      bk[k2] = (k2 > k && k2 < P.sc.n_lights) ? __ballot_sync(0xffffffffu, next == k2) : 0u;
+      counts[1 + k2] = __popc(bk[k2]);
+    }
+    reserve<true>(P, counts, P.sc.n_lights, k + 2, lane);
+#pragma unroll
+    for (int k2 = 0; k2 < RTB_MAX_LIGHTS; k2++) {
+      if (next == k2) {
+        const uint32_t e2 = counts[1 + k2] + __popc(bk[k2] & lanemask_lt());
+        const float4 ps = P.b.pos[node];
+        P.b.srec_a[k2][e2] = shadow_record(P, k2, ps.x, ps.y, ps.z);
+        P.b.srec_b[k2][e2] = make_int4((int)node, hit_i, __float_as_int(I), 0);
+      }
+    }
   }
 }
 
@@ -875,7 +1091,7 @@ wf_compose_kernel(const __grid_constant__ WfParams P, int level) {
     const uint32_t node = (uint32_t)i;
     float col[3];
     node_colour(P, node, col);
-    const int2 lk = P.b.link[node];
+    const int4 lk = P.b.link[node];
     const float wgt = P.b.ray_d[node].z;                  // parent's albedo[3] or albedo[4]
     const float4 v = make_float4(col[0] * wgt, col[1] * wgt, col[2] * wgt, 0.f);   // main.js:271, 277
     if (lk.y & 1) P.b.child_b[lk.x] = v; else P.b.child_a[lk.x] = v;
@@ -922,21 +1138,22 @@ wf_resolve_kernel(const __grid_constant__ WfParams P) {
 
 // ---- host side ------------------------------------------------------------------------------------------
 size_t per_node_bytes(int n_lights) {
-  return 16 * 7 + 8 + (n_lights > 2 ? 16 : 0) + 4 * (size_t)n_lights;
+  return 16 * 8 + (n_lights > 2 ? 16 : 0) + 4 * (size_t)n_lights;
 }
 
 void slot_free(WfSlot& sl) {
   WfBuffers& b = sl.wf;
   cudaFree(b.ray_o); cudaFree(b.ray_d); cudaFree(b.link); cudaFree(b.pos); cudaFree(b.base);
   cudaFree(b.lq); cudaFree(b.lq2); cudaFree(b.acc); cudaFree(b.child_a); cudaFree(b.child_b);
-  for (int k = 0; k < RTB_MAX_LIGHTS; k++) cudaFree(b.sq[k]);
+  for (int k = 0; k < RTB_MAX_LIGHTS; k++) { cudaFree(b.sq[k]); cudaFree(b.srec_a[k]); cudaFree(b.srec_b[k]); }
+  cudaFree(b.key);
   cudaFree(b.ctr);
   b = WfBuffers{};
   sl.wf_lights = 0;
   sl.wf_bytes = 0;
 }
 
-int ensure_workspace(WfSlot& sl, int n_lights, uint32_t cap_nodes) {
+int ensure_workspace(WfSlot& sl, int n_lights, uint32_t cap_nodes, bool split) {
   WfBuffers& b = sl.wf;
   if (!sl.stream2) {
     RTB_CUDA(cudaStreamCreateWithFlags(&sl.stream2, cudaStreamNonBlocking));
@@ -947,14 +1164,16 @@ int ensure_workspace(WfSlot& sl, int n_lights, uint32_t cap_nodes) {
     RTB_CUDA(cudaMallocHost(&sl.h_sticky, sizeof(WfSticky)));
   }
   const bool need_lq2 = n_lights > 2;
-  if (b.cap_nodes >= cap_nodes && b.ctr && sl.wf_lights >= n_lights && (!need_lq2 || b.lq2)) return RTB_OK;
+  if (b.cap_nodes >= cap_nodes && b.ctr && sl.wf_lights >= n_lights && (!need_lq2 || b.lq2) && (!split || b.key))
+    return RTB_OK;
+  split = split || b.key != nullptr;
   const uint32_t cap = std::max(cap_nodes, b.cap_nodes);
   const int lights = std::max(n_lights, sl.wf_lights);
   slot_free(sl);
   const size_t n = cap;
   RTB_CUDA(cudaMalloc(&b.ray_o, n * 16));
   RTB_CUDA(cudaMalloc(&b.ray_d, n * 16));
-  RTB_CUDA(cudaMalloc(&b.link, n * 8));
+  RTB_CUDA(cudaMalloc(&b.link, n * 16));
   RTB_CUDA(cudaMalloc(&b.pos, n * 16));
   RTB_CUDA(cudaMalloc(&b.base, n * 16));
   RTB_CUDA(cudaMalloc(&b.lq, n * 16));
@@ -963,10 +1182,17 @@ int ensure_workspace(WfSlot& sl, int n_lights, uint32_t cap_nodes) {
   RTB_CUDA(cudaMalloc(&b.child_a, n * 16));
   RTB_CUDA(cudaMalloc(&b.child_b, n * 16));
   for (int k = 0; k < lights; k++) RTB_CUDA(cudaMalloc(&b.sq[k], n * 4));
+  if (split) {
+    RTB_CUDA(cudaMalloc(&b.key, n * 8));
+    for (int k = 0; k < lights; k++) {
+      RTB_CUDA(cudaMalloc(&b.srec_a[k], n * 16));
+      RTB_CUDA(cudaMalloc(&b.srec_b[k], n * 16));
+    }
+  }
   RTB_CUDA(cudaMalloc(&b.ctr, sizeof(WfCounters) + sizeof(WfSticky)));
   b.cap_nodes = cap;
   sl.wf_lights = lights;
-  sl.wf_bytes = n * per_node_bytes(lights);
+  sl.wf_bytes = n * (per_node_bytes(lights) + (split ? 8 + 32 * (size_t)lights : 0));
   return RTB_OK;
 }
 
@@ -1091,7 +1317,15 @@ int wf_render(RtbScene_* s, const RtbCamera* cams, int n_frames, const DevFrameT
   if (const char* e = getenv("RTB_WF_CAP_NODES")) { const long long v = atoll(e); if (v > 0) cap = (uint64_t)v; }
   if (cap < 4 * sub_per_row) cap = 4 * sub_per_row;      // at least one row per band with headroom
   if (cap > 0xfffffff0ull) { rtb_set_error("frame too wide for the wavefront queues"); return RTB_ERR_UNSUPPORTED; }
-  int rc = ensure_workspace(sl, s->n_lights, (uint32_t)cap);
+  // Pipeline choice: RTB_WF_SPLIT=1 separates every level into a sweep kernel and a hit-processing kernel
+  // (and every light into an occluder sweep and a post kernel); 0 = the fused persistent kernels.
+  // bit 0: primary level, bit 1: levels >= 2 (sweep kernel + hit kernel instead of the fused trace kernel),
+  // bit 2: lights (occluder sweep from ray records + post kernel instead of the fused shadow kernel)
+  const char* split_env = getenv("RTB_WF_SPLIT");            // read per call: tests compare the pipelines
+  const int split_bits = (split_env ? atoi(split_env) : RTB_WF_SPLIT_DEFAULT) & 7;
+  const bool split_p = (split_bits & 1) != 0, split_s = (split_bits & 2) != 0, records = (split_bits & 4) != 0;
+  const bool split = split_bits != 0;
+  int rc = ensure_workspace(sl, s->n_lights, (uint32_t)cap, split);
   if (rc != RTB_OK) return rc;
   // the shared workspace may be larger than this call asked for; band sizes and the overflow
   // check follow the REQUESTED capacity so that results do not depend on earlier calls
@@ -1153,14 +1387,21 @@ int wf_render(RtbScene_* s, const RtbCamera* cams, int n_frames, const DevFrameT
     }
     return it->second * g_rtb.sm_count;
   };
+  typedef void (*LevelKernel)(WfParams, int);
+  const LevelKernel k_trace_p = records ? wf_trace_kernel<true, true> : wf_trace_kernel<true, false>;
+  const LevelKernel k_trace_s = records ? wf_trace_kernel<false, true> : wf_trace_kernel<false, false>;
+  const LevelKernel k_sweep_p = wf_sweep_kernel<true>, k_sweep_s = wf_sweep_kernel<false>;
+  const LevelKernel k_hit_p = records ? wf_hit_kernel<true, true> : wf_hit_kernel<true, false>;
+  const LevelKernel k_hit_s = records ? wf_hit_kernel<false, true> : wf_hit_kernel<false, false>;
   if (smem > 48 * 1024) {
-    RTB_CUDA(cudaFuncSetAttribute(wf_trace_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    RTB_CUDA(cudaFuncSetAttribute(wf_trace_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    RTB_CUDA(cudaFuncSetAttribute(wf_shadow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (const void* fn : {(const void*)k_trace_p, (const void*)k_trace_s, (const void*)k_sweep_p, (const void*)k_sweep_s,
+                           (const void*)wf_shadow_kernel, (const void*)wf_ssweep_kernel})
+      RTB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
-  const int grid_p = grid_for((const void*)wf_trace_kernel<true>, smem);
-  const int grid_s = grid_for((const void*)wf_trace_kernel<false>, smem);
-  const int grid_l = grid_for((const void*)wf_shadow_kernel, smem);
+  const int grid_p = grid_for((const void*)(split_p ? k_sweep_p : k_trace_p), smem);
+  const int grid_s = grid_for((const void*)(split_s ? k_sweep_s : k_trace_s), smem);
+  const int grid_l = grid_for(records ? (const void*)wf_ssweep_kernel : (const void*)wf_shadow_kernel, smem);
+  const int grid_h = split ? grid_for((const void*)k_hit_s, 0) : 0;
   const int grid_c = g_rtb.sm_count * 8;
 
   // bands are sized for 3 nodes per primary ray; RTB_WF_NODES_PER_RAY overrides (tests force a first overflow)
@@ -1207,8 +1448,14 @@ int wf_render(RtbScene_* s, const RtbCamera* cams, int n_frames, const DevFrameT
       RTB_CUDA(cudaMemsetAsync(sl.wf.ctr, 0, sizeof(WfCounters), st));
       if ((rc = mark(T_START)) != RTB_OK) return rc;
       wf_raygen_kernel<<<grid_c, WF_THREADS, 0, st>>>(P);
-      wf_trace_kernel<true><<<grid_p, WF_THREADS, smem, st>>>(P, 1);
-      launches += 2;
+      if (split_p) {
+        k_sweep_p<<<grid_p, WF_THREADS, smem, st>>>(P, 1);
+        k_hit_p<<<grid_h, WF_THREADS, 0, st>>>(P, 1);
+        launches += 3;
+      } else {
+        k_trace_p<<<grid_p, WF_THREADS, smem, st>>>(P, 1);
+        launches += 2;
+      }
       if ((rc = mark(T_PRIMARY)) != RTB_OK) return rc;
       // Without instrumentation the light-0 sweep of the level-1 nodes runs on a second stream,
       // concurrently with the secondary trace levels (independent work; fills their tails).
@@ -1216,13 +1463,25 @@ int wf_render(RtbScene_* s, const RtbCamera* cams, int n_frames, const DevFrameT
       if (overlap) {
         RTB_CUDA(cudaEventRecord(sl.ev_primary, st));
         RTB_CUDA(cudaStreamWaitEvent(sl.stream2, sl.ev_primary, 0));
-        wf_shadow_kernel<<<grid_l, WF_THREADS, smem, sl.stream2>>>(P, 0, 1);
-        launches++;
+        if (records) {
+          wf_ssweep_kernel<<<grid_l, WF_THREADS, smem, sl.stream2>>>(P, 0, 1);
+          wf_spost_kernel<<<grid_h, WF_THREADS, 0, sl.stream2>>>(P, 0, 1);
+          launches += 2;
+        } else {
+          wf_shadow_kernel<<<grid_l, WF_THREADS, smem, sl.stream2>>>(P, 0, 1);
+          launches++;
+        }
         RTB_CUDA(cudaEventRecord(sl.ev_early, sl.stream2));
       }
       for (int L = 2; L <= fr32.segs; L++) {
-        wf_trace_kernel<false><<<grid_s, WF_THREADS, smem, st>>>(P, L);
-        launches++;
+        if (split_s) {
+          k_sweep_s<<<grid_s, WF_THREADS, smem, st>>>(P, L);
+          k_hit_s<<<grid_h, WF_THREADS, 0, st>>>(P, L);
+          launches += 2;
+        } else {
+          k_trace_s<<<grid_s, WF_THREADS, smem, st>>>(P, L);
+          launches++;
+        }
       }
       if ((rc = mark(T_SECONDARY)) != RTB_OK) return rc;
       if (pipelined && l0 + rows_per_band >= n_rows) {       // last band: the next pass may start now
@@ -1231,8 +1490,15 @@ int wf_render(RtbScene_* s, const RtbCamera* cams, int n_frames, const DevFrameT
       }
       if (overlap) RTB_CUDA(cudaStreamWaitEvent(st, sl.ev_early, 0));
       for (int k = 0; k < s->n_lights; k++) {
-        wf_shadow_kernel<<<grid_l, WF_THREADS, smem, st>>>(P, k, (k == 0 && overlap) ? 2 : 0);
-        launches++;
+        const int phase = (k == 0 && overlap) ? 2 : 0;
+        if (records) {
+          wf_ssweep_kernel<<<grid_l, WF_THREADS, smem, st>>>(P, k, phase);
+          wf_spost_kernel<<<grid_h, WF_THREADS, 0, st>>>(P, k, phase);
+          launches += 2;
+        } else {
+          wf_shadow_kernel<<<grid_l, WF_THREADS, smem, st>>>(P, k, phase);
+          launches++;
+        }
       }
       if ((rc = mark(T_SHADOW)) != RTB_OK) return rc;
       for (int L = fr32.segs; L >= 2; L--) {

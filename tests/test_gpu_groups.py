@@ -236,3 +236,56 @@ def test_peer_scatter_group_on_one_device(rt, demo):
     finally:
         for p in frames + ctls:
             lib.rtb_peer_free(C.c_void_p(p))
+
+
+@pytest.mark.parametrize("scene", ["demo", "synth"])
+def test_split_pipeline_equals_fused_pipeline(rt, demo, synth, scene):
+    """The split pipeline (RTB_WF_SPLIT bits: sweep kernels + hit-processing kernels for the primary level /
+    the deeper levels, occluder sweeps from ray records + post kernels for the lights) and the fused persistent
+    kernels do the same arithmetic: byte-identical frames, identical device counters - whole frames, 4 spp with
+    star hash, ragged packed stripes, a moving-camera frame group, and tiny queues (many bands)."""
+    import torch
+    r = demo if scene == "demo" else synth
+    W, H = 256, 144
+    cam = rt.scenes.demo_camera(W, H)
+    cams = rt.scenes.orbit_cameras(W, H, 5)
+
+    def both(fn):
+        out = []
+        for split in ("0", "7"):
+            os.environ["RTB_WF_SPLIT"] = split
+            try:
+                out.append(fn())
+            finally:
+                del os.environ["RTB_WF_SPLIT"]
+        return out
+
+    kw = dict(segs=8, kernel=rt.RTB_KERNEL_WAVEFRONT)
+    (a, sa), (b, sb) = both(lambda: r.redraw(cam, stats=True, **kw))
+    assert np.array_equal(a, b)
+    for bits in ("1", "2", "4", "5"):                      # per stage: primary / deeper levels / lights
+        os.environ["RTB_WF_SPLIT"] = bits
+        try:
+            assert np.array_equal(r.redraw(cam, **kw), a), bits
+        finally:
+            del os.environ["RTB_WF_SPLIT"]
+    assert (sa.nodes, sa.shadow_rays, sa.sphere_tests) == (sb.nodes, sb.shadow_rays, sb.sphere_tests)
+    a, b = both(lambda: r.redraw(cam, spp_grid=2, star_mode=rt.RTB_STARS_HASH, star_seed=5, **kw))
+    assert np.array_equal(a, b)
+    a, b = both(lambda: r.redraw(cam, stripe_rows=3, stripe_rank=1, stripe_world=4, out_packed=1, **kw))
+    assert np.array_equal(a, b)
+    a, b = both(lambda: _group(rt, r, cams, H, W, **kw))
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    os.environ["RTB_WF_CAP_NODES"] = str(W * 5 * 10)
+    try:
+        with rt.Renderer(rt.scenes.demo_objects() if scene == "demo" else rt.scenes.synth_objects(160, 7)) as r2:
+            def banded():
+                st = rt._abi.RtbStats()
+                dev = torch.zeros((5, H, W, 4), dtype=torch.uint8, device="cuda")
+                r2.redraw_device_group(cams, rt.make_opts(**kw), [dev[i].data_ptr() for i in range(5)], stats=st)
+                return dev.cpu().numpy(), st.bands
+            (c, nb), (d, _) = both(banded)
+            assert nb > 1 and np.array_equal(c, d)
+            assert all(np.array_equal(c[i], a[i]) for i in range(5))
+    finally:
+        del os.environ["RTB_WF_CAP_NODES"]
