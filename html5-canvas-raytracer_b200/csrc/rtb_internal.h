@@ -171,7 +171,7 @@ int launch_pixel_f32(const DevSceneT<float>& sc, const DevFrameT<float>& fr, con
 //   product can only ADD candidates (the slow path re-decides exactly).  org inside the sphere: -inf
 //   (always a candidate); dummy: +inf.   exact[i] = (L, |L|^2 - r2) for the slow path.
 // wf_make_geom_table — general rays: (x,y,z) = C, w = -r2 (1 + 2e-6); test value d2 - r2' (main.js:424-425).
-constexpr int RTB_WF_GROUP = 16;
+constexpr int RTB_WF_GROUP = 32;
 inline int wf_pad(int n) { return (n + RTB_WF_GROUP - 1) / RTB_WF_GROUP * RTB_WF_GROUP; }
 inline void wf_pack(float4* tab, int i, float x, float y, float z, float w) {
   float* a = reinterpret_cast<float*>(&tab[2 * (i / 2)]);

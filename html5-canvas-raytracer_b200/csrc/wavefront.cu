@@ -96,7 +96,7 @@ constexpr int WF_THREADS = 256;
 #define WF_MIN_CTAS_SHADOW 2
 #endif
 #ifndef RTB_WF_SPLIT_DEFAULT
-#define RTB_WF_SPLIT_DEFAULT 0
+#define RTB_WF_SPLIT_DEFAULT 7
 #endif
 #ifndef WF_MIN_CTAS_SWEEP_PRIMARY
 #define WF_MIN_CTAS_SWEEP_PRIMARY 2
@@ -108,9 +108,13 @@ constexpr int WF_THREADS = 256;
 #define WF_MIN_CTAS_GENERAL 3            // general rays: 4 per lane fit 80 registers (measured 3.93 -> 3.66 ms per 4K frame)
 #endif
 constexpr float WF_INF = __builtin_huge_valf();
-constexpr int WF_GROUP = 8;              // spheres per candidate check; the unrolled body (4 sphere pairs x R
+constexpr int WF_CHECK = 32;             // spheres per CANDIDATE CHECK: the sign bits of 32 tests fill a ray's mask, and only
+                                         // then does the warp look at them (one OR + branch, and the per-ray visit of set
+                                         // bits if any) - with a check after every 8 the bookkeeping around the branch was
+                                         // ~13 % of the shadow sweep's and ~6 % of the trace sweeps' warp time
+constexpr int WF_GROUP = 8;              // spheres per unrolled body; the body (4 sphere pairs x R
                                          // rays) must stay well inside the ~6 KB L0 instruction cache
-static_assert(RTB_WF_GROUP % WF_GROUP == 0, "table padding must be a multiple of the sweep group");
+static_assert(RTB_WF_GROUP % WF_CHECK == 0 && WF_CHECK % WF_GROUP == 0, "table padding must be a multiple of the check interval");
 constexpr int R_SHARED = 8;              // rays per lane, shared-origin sweeps (primary, shadow)
 constexpr int R_GENERAL = 4;             // rays per lane, general sweep (reflect / refract rays)
 constexpr unsigned long long KEY_NONE = 0x7f800000ffffffffull;   // t = +inf, no sphere
@@ -191,7 +195,7 @@ __device__ __noinline__ unsigned long long slow_primary(const float4* __restrict
   while (m) {
     const int b = 31 - __clz((int)m);
     m ^= 1u << b;
-    const int jj = j + (8 - 1) - b;
+    const int jj = j + (WF_CHECK - 1) - b;
     const float4 x = exact[jj];
     const float tca = -(ndx * x.x + ndy * x.y + ndz * x.z);
     exact_update(tca, tca * tca - x.w, eps, jj, best);
@@ -210,7 +214,7 @@ __device__ __noinline__ unsigned long long slow_general(const float4* __restrict
   while (m) {
     const int b = 31 - __clz((int)m);
     m ^= 1u << b;
-    const int jj = j + (8 - 1) - b;
+    const int jj = j + (WF_CHECK - 1) - b;
     const float4 s = geom[jj];
     const float L0 = s.x + nox, L1 = s.y + noy, L2 = s.z + noz;
     const float tca = dx * L0 + dy * L1 + dz * L2;
@@ -239,7 +243,7 @@ __device__ __noinline__ float slow_shadow(const float4* __restrict__ exact, cons
   while (m) {
     const int b = 31 - __clz((int)m);
     m ^= 1u << b;
-    const int jj = j + (8 - 1) - b;
+    const int jj = j + (WF_CHECK - 1) - b;
     if (jj == hit_i) continue;                              // main.js:294 — no shadow on self
     const float4 x = exact[jj];
     const float tca = -(nwx * x.x + nwy * x.y + nwz * x.z);
@@ -268,25 +272,28 @@ RTB_DEVINL void sweep_primary(const float4* __restrict__ tab, const float4* __re
   uint32_t mask[R];
 #pragma unroll
   for (int q = 0; q < R; q++) { best[q] = KEY_NONE; mask[q] = 0; }
-  for (int j = j_begin; j < j_end; j += WF_GROUP) {
+  for (int j = j_begin; j < j_end; j += WF_CHECK) {
+#pragma unroll 1
+    for (int jg = j; jg < j + WF_CHECK; jg += WF_GROUP) {
 #pragma unroll
-    for (int u = 0; u < WF_GROUP / 2; u++) {
-      const float4 A = tab[j + 2 * u], B = tab[j + 2 * u + 1];
+      for (int u = 0; u < WF_GROUP / 2; u++) {
+        const float4 A = tab[jg + 2 * u], B = tab[jg + 2 * u + 1];
 #pragma unroll
-      for (int q = 0; q < R; q++) {
-        float2 t = __ffma2_rn(f2(nd[q][2], nd[q][2]), f2(B.x, B.y), f2(B.z, B.w));
-        t = __ffma2_rn(f2(nd[q][1], nd[q][1]), f2(A.z, A.w), t);
-        t = __ffma2_rn(f2(nd[q][0], nd[q][0]), f2(A.x, A.y), t);
-        mask[q] = push_sign(push_sign(mask[q], t.x), t.y);
+        for (int q = 0; q < R; q++) {
+          float2 t = __ffma2_rn(f2(nd[q][2], nd[q][2]), f2(B.x, B.y), f2(B.z, B.w));
+          t = __ffma2_rn(f2(nd[q][1], nd[q][1]), f2(A.z, A.w), t);
+          t = __ffma2_rn(f2(nd[q][0], nd[q][0]), f2(A.x, A.y), t);
+          mask[q] = push_sign(push_sign(mask[q], t.x), t.y);
+        }
       }
     }
-    uint32_t any = 0;
+    uint32_t any = 0;                                      // the 32 pushes have replaced every bit of every mask
 #pragma unroll
     for (int q = 0; q < R; q++) any |= mask[q];
-    if (any & 0xffu) {
+    if (any) {
 #pragma unroll
       for (int q = 0; q < R; q++) {
-        const uint32_t m = mask[q] & 0xffu;
+        const uint32_t m = mask[q];
         if (m && active[q]) best[q] = slow_primary(exact, j, m, nd[q][0], nd[q][1], nd[q][2], eps, best[q]);
       }
     }
@@ -307,10 +314,12 @@ RTB_DEVINL void sweep_general(const float4* __restrict__ tab, const float4* __re
   uint32_t mask[R];
 #pragma unroll
   for (int q = 0; q < R; q++) { best[q] = KEY_NONE; mask[q] = 0; }
-  for (int j = j_begin; j < j_end; j += WF_GROUP) {
+  for (int j = j_begin; j < j_end; j += WF_CHECK) {
+#pragma unroll 1
+    for (int jg = j; jg < j + WF_CHECK; jg += WF_GROUP) {
 #pragma unroll
     for (int p = 0; p < WF_GROUP / 2; p++) {
-      const float4 A = tab[j + 2 * p], B = tab[j + 2 * p + 1];
+      const float4 A = tab[jg + 2 * p], B = tab[jg + 2 * p + 1];
 #pragma unroll
       for (int q = 0; q < R; q++) {
         float2 a = __ffma2_rn(f2(u[q][2], u[q][2]), f2(B.x, B.y), f2(nku[q], nku[q]));
@@ -324,13 +333,14 @@ RTB_DEVINL void sweep_general(const float4* __restrict__ tab, const float4* __re
         mask[q] = push_sign(push_sign(mask[q], e.x), e.y);
       }
     }
+    }
     uint32_t any = 0;
 #pragma unroll
     for (int q = 0; q < R; q++) any |= mask[q];
-    if (any & 0xffu) {
+    if (any) {
 #pragma unroll
       for (int q = 0; q < R; q++) {
-        const uint32_t m = mask[q] & 0xffu;
+        const uint32_t m = mask[q];
         if (m && active[q]) best[q] = slow_general(geom, ray_o, ray_d, j, m, node[q], self[q], eps, best[q]);
       }
     }
@@ -874,43 +884,49 @@ RTB_DEVINL void shadow_chunks(const WfParams& P, int k, const float4* __restrict
         if (I[q] != 0.f) { nw[q][0] = -wx; nw[q][1] = -wy; nw[q][2] = -wz; }
       }
     }
-    for (int j = 0; j < n_pad; j += WF_GROUP) {
+    for (int j = 0; j < n_pad; j += WF_CHECK) {
       if ((j & 127) == 0) {                                 // all rays of the warp fully occluded?
         bool l = false;
 #pragma unroll
         for (int q = 0; q < R; q++) l |= (I[q] != 0.f);
         if (!__any_sync(0xffffffffu, l)) break;
-#pragma unroll
-        for (int q = 0; q < R; q++) if (I[q] != 0.f) my_tests += (unsigned long long)min(128, n - j);
       }
+#pragma unroll 1
+      for (int jg = j; jg < j + WF_CHECK; jg += WF_GROUP) {
 #pragma unroll
-      for (int u = 0; u < WF_GROUP / 2; u++) {
-        const float4 A = tab[j + 2 * u], B = tab[j + 2 * u + 1];
+        for (int u = 0; u < WF_GROUP / 2; u++) {
+          const float4 A = tab[jg + 2 * u], B = tab[jg + 2 * u + 1];
 #pragma unroll
-        for (int q = 0; q < R; q++) {
-          float2 t = __ffma2_rn(f2(nw[q][2], nw[q][2]), f2(B.x, B.y), f2(B.z, B.w));
-          t = __ffma2_rn(f2(nw[q][1], nw[q][1]), f2(A.z, A.w), t);
-          t = __ffma2_rn(f2(nw[q][0], nw[q][0]), f2(A.x, A.y), t);
-          mask[q] = push_sign(push_sign(mask[q], t.x), t.y);
+          for (int q = 0; q < R; q++) {
+            float2 t = __ffma2_rn(f2(nw[q][2], nw[q][2]), f2(B.x, B.y), f2(B.z, B.w));
+            t = __ffma2_rn(f2(nw[q][1], nw[q][1]), f2(A.z, A.w), t);
+            t = __ffma2_rn(f2(nw[q][0], nw[q][0]), f2(A.x, A.y), t);
+            mask[q] = push_sign(push_sign(mask[q], t.x), t.y);
+          }
         }
       }
       uint32_t any = 0;
 #pragma unroll
       for (int q = 0; q < R; q++) any |= mask[q];
-      if (any & 0xffu) {
+      if (any) {
 #pragma unroll
         for (int q = 0; q < R; q++) {
-          uint32_t m = mask[q] & 0xffu;
+          uint32_t m = mask[q];
           // the ray ends ON sphere hit_i, so that sphere is always a candidate; drop its bit here
           // (main.js:294 skips it) instead of paying a divergent slow-path call to find that out
-          if (j == (hit_i[q] & ~(WF_GROUP - 1))) m &= ~(0x80u >> (hit_i[q] & (WF_GROUP - 1)));
+          if (j == (hit_i[q] & ~(WF_CHECK - 1))) m &= ~(0x80000000u >> (hit_i[q] & (WF_CHECK - 1)));
           if (m && I[q] != 0.f) {
             I[q] = slow_shadow(exact, P.sc.mtl, j, m, nw[q][0], nw[q][1], nw[q][2], len[q], hit_i[q], eps, I[q]);
-            if (I[q] == 0.f) nw[q][0] = nw[q][1] = nw[q][2] = 0.f;   // fully occluded: stop testing
+            if (I[q] == 0.f) {                               // fully occluded: stop testing
+              nw[q][0] = nw[q][1] = nw[q][2] = 0.f;
+              my_tests += (unsigned long long)min(j + WF_CHECK, n);   // device statistic: spheres swept while lit
+            }
           }
         }
       }
     }
+#pragma unroll
+    for (int q = 0; q < R; q++) if (active[q] && I[q] != 0.f) my_tests += (unsigned long long)n;
     if (SPLIT) {                                            // wf_spost_kernel accumulates and hands on
 #pragma unroll
       for (int q = 0; q < R; q++)
