@@ -115,8 +115,14 @@ constexpr int WF_CHECK = 32;             // spheres per CANDIDATE CHECK: the sig
 constexpr int WF_GROUP = 8;              // spheres per unrolled body; the body (4 sphere pairs x R
                                          // rays) must stay well inside the ~6 KB L0 instruction cache
 static_assert(RTB_WF_GROUP % WF_CHECK == 0 && WF_CHECK % WF_GROUP == 0, "table padding must be a multiple of the check interval");
-constexpr int R_SHARED = 8;              // rays per lane, shared-origin sweeps (primary, shadow)
-constexpr int R_GENERAL = 4;             // rays per lane, general sweep (reflect / refract rays)
+#ifndef WF_R_SHARED
+#define WF_R_SHARED 8
+#endif
+#ifndef WF_R_GENERAL
+#define WF_R_GENERAL 4
+#endif
+constexpr int R_SHARED = WF_R_SHARED;    // rays per lane, shared-origin sweeps (primary, shadow)
+constexpr int R_GENERAL = WF_R_GENERAL;  // rays per lane, general sweep (reflect / refract rays)
 constexpr unsigned long long KEY_NONE = 0x7f800000ffffffffull;   // t = +inf, no sphere
 constexpr int WF_WARPS = WF_THREADS / 32;
 
