@@ -396,7 +396,10 @@ def main():
     #     every frame copied into pinned host memory (D2H under the kernels of the next frames), destroy.
     #     N = 1: ONE C-ABI call, rtb_render_batch.  N > 1: StripedRenderer.redraw_sequence, rank 0 reads back.
     kb = max(4, min(args.steps, 40))                    # 40 x 33 MB of pinned host memory at 4K
-    host_seq = torch.empty((kb, H, W, 4), dtype=torch.uint8).pin_memory() if rank == 0 else None
+    host_seq = torch.empty((kb, H, W, 4), dtype=torch.uint8).pin_memory() if (rank == 0 and world <= 1) else None
+    # N > 1: the frames land in ONE ring of host framebuffers in shared memory that every rank has mapped and
+    # page-locked; each rank copies its own rows of every frame over its own PCIe link (SharedHostFrames)
+    ring = mg.SharedHostFrames(kb, H, W, rank, world) if world > 1 else None
     cams_c = (A.RtbCamera * kb)(*([cam_c] * kb))
 
     def e2e_sequence():
@@ -410,13 +413,11 @@ def main():
                 old = sr.r._h
                 sr.r._h = h
                 try:
-                    def to_host(j, frame):
-                        if rank == 0:
-                            host_seq[j].copy_(frame, non_blocking=True)    # on the frame's own stream
-                    sr.redraw_sequence([cam] * kb, on_frame=to_host, frames_in_flight=fif, **opts_kw)
+                    sr.redraw_sequence([cam] * kb, frames_in_flight=fif, host_frames=ring, **opts_kw)
                 finally:
                     sr.r._h = old
                 torch.cuda.synchronize()
+                dist.barrier()                           # every rank's rows of every frame are in host memory
             e2e_launches += pass_launches * len(mg.split_groups(kb, G))
         finally:
             lib.rtb_scene_destroy(h)
@@ -434,6 +435,8 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_ms, single_ms = float(te[0].item()), float(te[1].item())
     e2e_value = rays_per_frame / (e2e_ms * 1e-3) / 1e6
+    if ring is not None:
+        ring.close()
 
     clocks = sampler.stop() if sampler else {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
     if mode == "device" and dev_mhz_min < 1e8:
@@ -520,9 +523,11 @@ def main():
                 "what": f"a sequence of {kb} frames through the host API, all inside the timed region: rtb_scene_create "
                         "(the whole scene description from host memory, H2D once per sequence: "
                         f"{h2d_bytes} B) + " +
-                        ("ONE rtb_render_batch call" if world == 1 else "StripedRenderer.redraw_sequence") +
-                        " (every frame D2H into pinned host memory, under the kernels of the next frames) + "
-                        "rtb_scene_destroy",
+                        ("ONE rtb_render_batch call (every frame D2H into pinned host memory, under the kernels of the "
+                         "next frames)" if world == 1 else
+                         "StripedRenderer.redraw_sequence into a ring of host framebuffers in shared, page-locked memory: "
+                         "every rank copies its own rows of every frame over its own PCIe link (rtb_stripe_rows_to_host), "
+                         "barrier at the end") + " + rtb_scene_destroy",
                 "single_frame": {"ms": round(single_ms, 4), "value": round(rays_per_frame / (single_ms * 1e-3) / 1e6, 2),
                                  "what": "one frame per call: rtb_scene_create + rtb_render into a pinned host buffer "
                                          "+ rtb_scene_destroy (nothing overlaps)"}},

@@ -122,7 +122,8 @@ EXPORTS = [
     "rtb_peer_alloc", "rtb_peer_open", "rtb_peer_close", "rtb_peer_free", "rtb_peer_scatter", "rtb_peer_scatter_group", "rtb_peer_signal", "rtb_peer_wait", "rtb_render",
     "rtb_render_device", "rtb_render_device_group", "rtb_render_batch", "rtb_unstripe_device", "rtb_stripe_local_rows",
     "rtb_stripe_padded_rows", "rtb_default_opts", "rtb_last_error", "rtb_version",
-    "rtb_abi_version", "rtb_device_info", "rtb_clock_probe",
+    "rtb_abi_version", "rtb_device_info", "rtb_clock_probe", "rtb_stripe_rows_to_host", "rtb_host_register",
+    "rtb_host_unregister",
 ]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -190,6 +191,10 @@ def load() -> C.CDLL:
     lib.rtb_abi_version.argtypes = []; lib.rtb_abi_version.restype = C.c_uint32
     lib.rtb_device_info.argtypes = [C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_char_p, C.c_int32]
     lib.rtb_device_info.restype = C.c_int
+    lib.rtb_stripe_rows_to_host.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]
+    lib.rtb_stripe_rows_to_host.restype = C.c_int
+    lib.rtb_host_register.argtypes = [vp, C.c_uint64]; lib.rtb_host_register.restype = C.c_int
+    lib.rtb_host_unregister.argtypes = [vp]; lib.rtb_host_unregister.restype = C.c_int
     lib.rtb_clock_probe.argtypes = [vp, C.c_int32, vp]; lib.rtb_clock_probe.restype = C.c_int
     _lib = lib
     return lib

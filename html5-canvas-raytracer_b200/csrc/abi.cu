@@ -1,6 +1,7 @@
 // abi.cu — implementation of include/rtb200.h: device setup, scene upload, the render entry points
 // (host buffer, device buffer, frame batch), stripe bookkeeping for the multi-GPU layer, errors.
 // No CPU fallback anywhere: without a CUDA device every computing entry point fails.
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -861,6 +862,54 @@ int rtb_unstripe_device(const void* d_gathered, void* d_frame, int32_t width, in
   unstripe_kernel<<<g_rtb.sm_count * 8, 256, 0, st>>>((const uint32_t*)d_gathered, (uint32_t*)d_frame, width,
                                                      height, stripe_rows, stripe_world, padded);
   RTB_CUDA(cudaGetLastError());
+  return RTB_OK;
+}
+
+int rtb_stripe_rows_to_host(const void* d_packed, void* h_frame, int32_t width, int32_t height, int32_t stripe_rows,
+                            int32_t stripe_rank, int32_t stripe_world, void* cuda_stream) {
+  RTB_API_LOCK();
+  if (!g_rtb.inited) { rtb_set_error("rtb_init() has not been called"); return RTB_ERR_NOT_INIT; }
+  if (!d_packed || !h_frame || width <= 0 || height <= 0 || stripe_world < 1 ||
+      (stripe_world > 1 && (stripe_rows <= 0 || stripe_rank < 0 || stripe_rank >= stripe_world))) {
+    rtb_set_error("bad stripe copy arguments");
+    return RTB_ERR_INVALID;
+  }
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : g_rtb.stream;
+  const size_t row_bytes = (size_t)width * 4;
+  const uint8_t* src = static_cast<const uint8_t*>(d_packed);
+  uint8_t* dst = static_cast<uint8_t*>(h_frame);
+  if (stripe_world <= 1) {
+    RTB_CUDA(cudaMemcpyAsync(dst, src, row_bytes * (size_t)height, cudaMemcpyDeviceToHost, st));
+    return RTB_OK;
+  }
+  // stripe i of this rank = rows [(i * world + rank) * S, +S): full stripes as ONE strided 2-D copy (packed
+  // source pitch S rows, destination pitch S * world rows), a ragged last stripe on its own
+  const int S = stripe_rows, period = S * stripe_world;
+  const int first = stripe_rank * S;
+  if (first >= height) return RTB_OK;
+  const int full = (height - first) / period + (((height - first) % period) >= S ? 1 : 0);   // complete stripes
+  if (full > 0)
+    RTB_CUDA(cudaMemcpy2DAsync(dst + row_bytes * first, row_bytes * period, src, row_bytes * S, row_bytes * S,
+                               (size_t)full, cudaMemcpyDeviceToHost, st));
+  const int y_tail = first + full * period;                  // a stripe cut short by the frame's last row
+  if (y_tail < height) {
+    const int rows = std::min(S, height - y_tail);
+    RTB_CUDA(cudaMemcpyAsync(dst + row_bytes * y_tail, src + row_bytes * (size_t)full * S, row_bytes * rows,
+                             cudaMemcpyDeviceToHost, st));
+  }
+  return RTB_OK;
+}
+
+int rtb_host_register(void* p, uint64_t bytes) {
+  if (!g_rtb.inited) { rtb_set_error("rtb_init() has not been called"); return RTB_ERR_NOT_INIT; }
+  if (!p || bytes == 0) { rtb_set_error("NULL argument"); return RTB_ERR_INVALID; }
+  RTB_CUDA(cudaHostRegister(p, (size_t)bytes, cudaHostRegisterPortable));
+  return RTB_OK;
+}
+
+int rtb_host_unregister(void* p) {
+  if (!p) return RTB_OK;
+  RTB_CUDA(cudaHostUnregister(p));
   return RTB_OK;
 }
 

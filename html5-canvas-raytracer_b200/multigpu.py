@@ -117,6 +117,58 @@ _CTL_READY, _CTL_STATUS, _CTL_ACK, _CTL_TIMEOUT, _CTL_WORDS = 0, 128, 256, 384, 
 _PEER_TIMEOUT_MS = int(os.environ.get("RTB_PEER_TIMEOUT_MS", "20000"))
 
 
+class SharedHostFrames:
+    """A ring of full host framebuffers ([n, H, W, 4] uint8) in POSIX shared memory that EVERY rank's process
+    has mapped and page-locked.  In a striped sequence each rank then copies its own rows of every frame straight
+    from its GPU into the frames (rtb_stripe_rows_to_host): the N GPUs of a box deliver a frame over their N PCIe
+    links at once, instead of funnelling 33 MB per 4K frame through one GPU's link after the NVLink exchange.
+    The consumer (any of the processes, or a host process that maps the same segment) reads `frames`.
+    Collective: every rank constructs it and every rank calls close()."""
+
+    def __init__(self, n: int, height: int, width: int, rank: int, world: int):
+        import torch.distributed as dist
+        from multiprocessing import resource_tracker, shared_memory
+
+        self.n, self.H, self.W, self.rank, self.world = n, height, width, rank, world
+        self.frame_bytes = height * width * 4
+        size = max(1, n * self.frame_bytes)
+        name = [None]
+        if rank == 0:
+            self.shm = shared_memory.SharedMemory(create=True, size=size)
+            name[0] = self.shm.name
+        if world > 1:
+            dist.broadcast_object_list(name, src=0)
+        if rank != 0:
+            self.shm = shared_memory.SharedMemory(name=name[0], create=False)
+            try:                                          # attaching is not owning: only rank 0 unlinks
+                resource_tracker.unregister(self.shm._name, "shared_memory")
+            except Exception:
+                pass
+        self.frames = np.ndarray((n, height, width, 4), dtype=np.uint8, buffer=self.shm.buf)
+        self.base = self.frames.ctypes.data
+        self.lib = A.load()
+        A.check(self.lib.rtb_host_register(C.c_void_p(self.base), size))
+        if world > 1:
+            dist.barrier()
+
+    def ptr(self, i: int) -> int:
+        return self.base + (i % self.n) * self.frame_bytes
+
+    def close(self):
+        import torch.distributed as dist
+
+        if getattr(self, "shm", None) is None:
+            return
+        self.lib.rtb_host_unregister(C.c_void_p(self.base))
+        self.frames = None
+        if self.world > 1:
+            dist.barrier()
+        self.shm.close()
+        if self.rank == 0:
+            self.shm.unlink()
+        self.shm = None
+
+
 class StripedRenderer:
     """Row-stripe sharded redraw(): every rank ends up with the full framebuffer on its GPU.
 
@@ -305,9 +357,11 @@ class StripedRenderer:
             A.check(self.lib.rtb_peer_signal(P["ctl"], self.world, self.rank, _CTL_ACK + 16 * slot, P["unacked"][slot], st))
             P["unacked"][slot] = 0
 
-    def _enqueue_scatter(self, slot, n):
+    def _enqueue_scatter(self, slot, n, host=None, first_frame=0):
         """p2p: wait until every peer has released the framebuffers of `slot`, store this rank's rows of the
-        group's n frames into all of them, wait until every rank's rows have arrived here."""
+        group's n frames into all of them, wait until every rank's rows have arrived here.  With `host`, the
+        rank's rows also leave for the shared host frames right behind the scatter kernel (PCIe, copy engine),
+        while the stream waits for the peers."""
         import torch
 
         P = self._peer
@@ -325,6 +379,8 @@ class StripedRenderer:
                                                 self.S, self.rank, self.world,
                                                 C.c_void_p(loc[0, self.padded].data_ptr()),
                                                 _CTL_READY + 16 * slot, _CTL_STATUS + 16 * slot, seq, st))
+        if host is not None:
+            self._enqueue_rows_to_host(slot, n, host, first_frame)
         A.check(self.lib.rtb_peer_wait(C.c_void_p(ctl + 4 * (_CTL_READY + 16 * slot)), self.world, seq,
                                        _PEER_TIMEOUT_MS, tflag, st))
         P["slot_seq"][slot] = seq
@@ -342,7 +398,18 @@ class StripedRenderer:
             ev.record()
             tr[name] = (ev, time.perf_counter())
 
-    def _enqueue_group(self, cams, slot, kw, stats=None, tr=None):
+    def _enqueue_rows_to_host(self, slot, n, host, first_frame):
+        """This rank's rows of the group's n frames -> the shared host frames first_frame .. (one strided D2H per
+        frame, on the current stream, straight from the packed stripe buffers / world 1: the framebuffers)."""
+        import torch
+
+        st = A.stream_arg(torch.cuda.current_stream().cuda_stream)
+        for b in range(n):
+            src = self.frames[slot][b] if self.world <= 1 else self.local[slot][b]
+            A.check(self.lib.rtb_stripe_rows_to_host(C.c_void_p(src.data_ptr()), C.c_void_p(host.ptr(first_frame + b)),
+                                                     self.W, self.H, self.S, self.rank, max(self.world, 1), st))
+
+    def _enqueue_group(self, cams, slot, kw, stats=None, tr=None, host=None, first_frame=0):
         """Render + exchange of one group of frames into self.frames[slot][0..n); status words to the host."""
         n = len(cams)
         if n > self.G:
@@ -352,12 +419,16 @@ class StripedRenderer:
             self._enqueue_release(slot)
         self._enqueue_render(cams, slot, stats, kw)
         self._mark(tr, "rendered")
+        if host is not None and self.exchange == "nccl":
+            self._enqueue_rows_to_host(slot, n, host, first_frame)
         if self.exchange == "p2p":
-            self._enqueue_scatter(slot, n)
+            self._enqueue_scatter(slot, n, host, first_frame)
         elif self.exchange == "nccl":
             self._enqueue_gather(slot).wait()             # stream-level wait, the host does not block
             self._enqueue_unstripe(slot, n)
         else:
+            if host is not None:
+                self._enqueue_rows_to_host(slot, n, host, first_frame)
             self.flags_host[slot][:1].copy_(self.status_dev[slot, :1], non_blocking=True)
 
     def _frame_ok(self, slot) -> bool:
@@ -394,7 +465,8 @@ class StripedRenderer:
         raise self._overflow_error()
 
     # -- a sequence of frames (throughput mode) ----------------------------------------------------------
-    def redraw_sequence(self, cameras, on_frame=None, frames_in_flight: int = 0, group: int = 0, trace=None, **kw):
+    def redraw_sequence(self, cameras, on_frame=None, frames_in_flight: int = 0, group: int = 0, trace=None,
+                        host_frames=None, **kw):
         """Software-pipelined: the sequence is cut into groups of up to `group` frames (0 = this renderer's group
         size; one wavefront pass each) and up to `frames_in_flight` passes (0 = default_in_flight(world)) are
         enqueued before the host waits for the oldest one, each on its own stream with its own library workspace.
@@ -402,8 +474,14 @@ class StripedRenderer:
         GPU.  `on_frame(i, frame)` is called (device tensor, valid until `frames_in_flight - 1` further groups
         have been issued) once frame i is assembled on this rank.  Returns the number of groups that had to be
         repeated because of queue overflows (every rank reads the same status words, so every rank repeats the
-        same groups); more than MAX_REPEATS raise RtbError(RTB_ERR_OVERFLOW)."""
+        same groups); more than MAX_REPEATS raise RtbError(RTB_ERR_OVERFLOW).
+        `host_frames` (a SharedHostFrames of at least len(cameras) frames, constructed by every rank): every rank
+        also copies ITS rows of frame i into host_frames.frames[i]; when the call returns on every rank (the caller
+        puts a barrier behind it), the frames are complete in host memory."""
         import torch
+
+        if host_frames is not None and host_frames.n < len(cameras):
+            raise ValueError("host_frames holds fewer frames than the sequence")
 
         depth = max(1, min(self.K, int(frames_in_flight) or default_in_flight(self.world)))
         sizes = split_groups(len(cameras), max(1, min(self.G, int(group) or self.G)))
@@ -428,7 +506,8 @@ class StripedRenderer:
                         if trace is not None:
                             tr = {"group": i, "frames": sizes[i]}
                             trace.append(tr)
-                        self._enqueue_group(cameras[starts[i]:starts[i] + sizes[i]], slot, kw, tr=tr)
+                        self._enqueue_group(cameras[starts[i]:starts[i] + sizes[i]], slot, kw, tr=tr,
+                                            host=host_frames, first_frame=starts[i])
                         self._mark(tr, "done")
                         done[slot].record()
                     inflight.append(i)

@@ -289,6 +289,16 @@ int rtb_peer_signal(void* const* peer_ctl, int32_t world, int32_t rank, uint32_t
 int rtb_peer_wait(const void* d_words_u32, int32_t n, uint32_t value, uint32_t timeout_ms, void* d_timeout_flag_u32,
                   void* cuda_stream);
 
+/* Multi-GPU host delivery: copy this rank's PACKED stripe rows (device) to their natural rows of a full
+ * width*height*4 HOST frame, asynchronously on `cuda_stream` (one strided 2-D copy).  With a frame in host memory
+ * that every rank's process has mapped and page-locked (POSIX shared memory + rtb_host_register), the N ranks of
+ * a box deliver a frame over their N PCIe links at once instead of funnelling it through one GPU's link.
+ * rtb_host_register / rtb_host_unregister page-lock caller-owned host memory (cudaHostRegister, portable). */
+int rtb_stripe_rows_to_host(const void* d_packed, void* h_frame, int32_t width, int32_t height, int32_t stripe_rows,
+                            int32_t stripe_rank, int32_t stripe_world, void* cuda_stream);
+int rtb_host_register(void* p, uint64_t bytes);
+int rtb_host_unregister(void* p);
+
 /* Number of rows rank `stripe_rank` owns / the padded per-rank row count used by the gather. */
 int32_t rtb_stripe_local_rows(int32_t height, int32_t stripe_rows, int32_t stripe_rank,
                               int32_t stripe_world);

@@ -289,3 +289,53 @@ def test_split_pipeline_equals_fused_pipeline(rt, demo, synth, scene):
             assert all(np.array_equal(c[i], a[i]) for i in range(5))
     finally:
         del os.environ["RTB_WF_CAP_NODES"]
+
+
+@pytest.mark.parametrize("S,H", [(1, 70), (4, 70), (4, 64), (8, 21)])
+def test_stripe_rows_to_host_assembles_the_frame(rt, demo, S, H):
+    """rtb_stripe_rows_to_host: every 'rank' copies its packed stripe rows from the device to their natural
+    rows of ONE host frame (page-locked with rtb_host_register) - complete stripes as one strided 2-D copy, a
+    ragged last stripe on its own; together the ranks' copies are the whole frame."""
+    import torch
+    A = rt._abi
+    lib = A.load()
+    W, world = 96, 3
+    cam = rt.scenes.demo_camera(W, H)
+    full = demo.redraw(cam)
+    host = np.zeros((H, W, 4), np.uint8)
+    A.check(lib.rtb_host_register(C.c_void_p(host.ctypes.data), host.nbytes))
+    try:
+        for rank in range(world):
+            rows = lib.rtb_stripe_local_rows(H, S, rank, world)
+            dev = torch.zeros((max(rows, 1), W, 4), dtype=torch.uint8, device="cuda")
+            if rows:
+                demo.redraw_device(cam, rt.make_opts(stripe_rows=S, stripe_rank=rank, stripe_world=world, out_packed=1),
+                                   dev.data_ptr())
+            A.check(lib.rtb_stripe_rows_to_host(C.c_void_p(dev.data_ptr()), C.c_void_p(host.ctypes.data), W, H, S,
+                                                rank, world, None))
+            torch.cuda.synchronize()
+        assert demo.finish()
+        assert np.array_equal(host, full)
+    finally:
+        lib.rtb_host_unregister(C.c_void_p(host.ctypes.data))
+    assert lib.rtb_stripe_rows_to_host(None, C.c_void_p(host.ctypes.data), W, H, S, 0, world, None) == A.RTB_ERR_INVALID
+
+
+def test_sequence_into_shared_host_frames(rt, synth):
+    """redraw_sequence(host_frames=...): every frame of the sequence lands in the shared, page-locked host ring."""
+    import torch
+    mg = importlib.import_module("html5-canvas-raytracer_b200.multigpu")
+    W, H = 160, 90
+    cams = rt.scenes.orbit_cameras(W, H, 7)
+    kw = dict(segs=6, kernel=rt.RTB_KERNEL_WAVEFRONT)
+    refs = [synth.redraw(c, **kw) for c in cams]
+    sr = mg.StripedRenderer(synth, W, H, 0, 1, group=3, slots=3)
+    ring = mg.SharedHostFrames(7, H, W, 0, 1)
+    try:
+        rep = sr.redraw_sequence(cams, frames_in_flight=2, host_frames=ring, **kw)
+        torch.cuda.synchronize()
+        assert rep == 0
+        for i in range(7):
+            assert np.array_equal(ring.frames[i], refs[i]), i
+    finally:
+        ring.close()

@@ -42,6 +42,16 @@ with rt.Renderer(objs, device=local_rank) as r:
                 same_as = [k for k in range(len(cams)) if np.array_equal(got[i], refs[k])]
                 print(f"rank {rank}:   frame {i}: {len(bad)} px differ, {len(rows)} rows, owner ranks {owners}, equals ref of frame {same_as}", flush=True)
     ok &= all(seq_ok) and rep == 0
+    # host delivery: every rank copies its own rows into a shared, page-locked host ring
+    ring = mg.SharedHostFrames(len(cams), H, W, rank, world)
+    rep_h = sr.redraw_sequence(cams, host_frames=ring, **kw)
+    torch.cuda.synchronize()
+    dist.barrier()
+    host_ok = [bool(np.array_equal(ring.frames[i], refs[i])) for i in range(len(cams))]
+    if not all(host_ok) or rep_h:
+        print(f"rank {rank}: shared host frames ok={host_ok} repeats={rep_h}", flush=True)
+    ok &= all(host_ok) and rep_h == 0
+    ring.close()
     # force an overflow on the LAST rank only: the verdict travels in the gather payload
     if rank == world - 1:                                  # bands sized for 1.1 nodes per ray: the first attempt overflows,
         os.environ["RTB_WF_CAP_NODES"] = str(W * 9 * mg.default_group(world))   # halved bands (2.2, 4.4 ...) fit
