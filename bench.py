@@ -470,20 +470,23 @@ def main():
         return {"ms": round(ms, 4), "tests": int(tests / world),
                 "tflops": round(FLOPS_PER_TEST * tests / world / (ms * 1e-3) / 1e12, 3) if ms > 0 else None}
 
-    kernels = {"wf_trace_kernel<primary>": cls(st_acc["p"], T_primary),
-               "wf_trace_kernel<secondary>": cls(st_acc["s"], T_secondary),
-               "wf_shadow_kernel": cls(st_acc["sh"], T_shadow),
-               "wf_compose+resolve": {"ms": round(st_acc["c"] / K, 4)}}
+    # kernel classes of the split pipeline (csrc/wavefront.cu): a sweep kernel + a hit / post kernel per level / light
+    K_PRIMARY = "level 1: wf_raygen_kernel + wf_sweep_kernel<primary> + wf_hit_kernel<primary>"
+    K_SECOND = "levels 2..segs: wf_sweep_kernel<general> + wf_hit_kernel<general>"
+    K_LIGHTS = "lights: wf_ssweep_kernel + wf_spost_kernel"
+    kernels = {K_PRIMARY: cls(st_acc["p"], T_primary),
+               K_SECOND: cls(st_acc["s"], T_secondary),
+               K_LIGHTS: cls(st_acc["sh"], T_shadow),
+               "wf_compose_kernel + wf_resolve_kernel": {"ms": round(st_acc["c"] / K, 4)}}
     kernel_ms = (st_acc["p"] + st_acc["s"] + st_acc["sh"] + st_acc["c"]) / K
-    dom = max(("wf_trace_kernel<primary>", "wf_trace_kernel<secondary>", "wf_shadow_kernel"),
-              key=lambda k: kernels[k]["ms"])
+    dom = max((K_PRIMARY, K_SECOND, K_LIGHTS), key=lambda k: kernels[k]["ms"])
     if not use_wf:                      # one fused kernel per frame
         kernels = {"pixel_kernel<float>": cls(st_acc["k"], T)}
         kernel_ms = st_acc["k"] / K
         dom = "pixel_kernel<float>"
     # DRAM bytes of one launch of the dominant kernel, from the committed ncu --set full capture
     traffic, traffic_note = None, "no ncu capture for this workload"
-    tp = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic.json")
+    tp = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r02_traffic.json")
     if use_wf and CONFIG == "c3_synth1024_4k" and os.path.exists(tp):
         tj = json.load(open(tp))
         traffic = tj["dram_bytes_per_launch"]
