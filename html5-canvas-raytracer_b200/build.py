@@ -27,6 +27,7 @@ SOURCES = {
     "pixel_f32.cu": [],
     "wavefront.cu": [],
     "peer.cu": [],
+    "host_prep.cu": ["-Xcompiler", "-ffp-contract=off"],   # float64 host code, one rounding per JS operator
 }
 HEADERS = ["rtb_device.cuh", "rtb_internal.h", "pixel_kernel.cuh", "pixel_launch.inl",
            os.path.join(INCLUDE, "rtb200.h")]

@@ -2,6 +2,7 @@
 //
 //   const rtb = require('./rtb200.node');
 //   rtb.render(scene, camera, opts, colorbuf.data);      // fills the Uint8ClampedArray in place
+//   await rtb.renderAsync(scene, camera, opts, colorbuf.data);   // same on a worker thread, returns a Promise
 //
 // It replaces the pixel loops of main.js's redraw()/spanish() (main.js:180-199): JavaScript hands over
 // the same scene description main() builds (main.js:85-163) and gets back the bytes it would have
@@ -56,6 +57,23 @@ napi_status napi_create_double(napi_env, double value, napi_value* result);
 napi_status napi_create_string_utf8(napi_env, const char* str, size_t length, napi_value* result);
 napi_status napi_get_undefined(napi_env, napi_value* result);
 napi_status napi_throw_error(napi_env, const char* code, const char* msg);
+// promise-returning render (renderAsync): libuv worker + deferred
+typedef struct napi_deferred__* napi_deferred;
+typedef struct napi_async_work__* napi_async_work;
+typedef struct napi_ref__* napi_ref;
+typedef void (*napi_async_execute_callback)(napi_env env, void* data);
+typedef void (*napi_async_complete_callback)(napi_env env, napi_status status, void* data);
+napi_status napi_create_promise(napi_env, napi_deferred* deferred, napi_value* promise);
+napi_status napi_resolve_deferred(napi_env, napi_deferred deferred, napi_value resolution);
+napi_status napi_reject_deferred(napi_env, napi_deferred deferred, napi_value rejection);
+napi_status napi_create_error(napi_env, napi_value code, napi_value msg, napi_value* result);
+napi_status napi_create_async_work(napi_env, napi_value async_resource, napi_value async_resource_name,
+                                   napi_async_execute_callback execute, napi_async_complete_callback complete,
+                                   void* data, napi_async_work* result);
+napi_status napi_queue_async_work(napi_env, napi_async_work work);
+napi_status napi_delete_async_work(napi_env, napi_async_work work);
+napi_status napi_create_reference(napi_env, napi_value value, uint32_t initial_refcount, napi_ref* result);
+napi_status napi_delete_reference(napi_env, napi_ref ref);
 }
 #define NAPI_AUTO_LENGTH SIZE_MAX
 
@@ -130,22 +148,36 @@ void read_texels(napi_env env, napi_value t, size_t want, std::vector<uint8_t>& 
 // render(scene, camera, opts, out): scene = { objects: [{origin, r2, mtl:{color, albedo, specular_exponent,
 // refract_index, sampler_kind?, texture_unit?, checker_freq?, checker_color?, star_threshold?, star_gain?}}],
 // textures: [{width, height, texels}], lights?, light_intensity?, eps? }
-napi_value Render(napi_env env, napi_callback_info info) {
-  napi_value undef;
-  napi_get_undefined(env, &undef);
-  rtb_scene_t scene = nullptr;
-  try {
-    size_t argc = 4;
-    napi_value argv[4];
-    NAPI_OK(napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
-    if (argc < 4) throw Fail{"render(scene, camera, opts, out) takes 4 arguments"};
+//
+// A call is three steps: marshal() walks the JS objects (main thread only), run() talks to the C ABI and
+// touches no JS value (any thread), result() builds the stats object (main thread).  render() does them in a
+// row; renderAsync() runs the middle one on a libuv worker and returns a Promise, so that the page keeps its
+// event loop - the reason the reference renders one scanline per setTimeout tick (main.js:182, 201).
+struct Job {
+  std::vector<RtbSphere> spheres;
+  std::vector<RtbTexture> textures;
+  std::vector<std::vector<uint8_t>> texel_store;
+  RtbSceneDesc desc;
+  RtbCamera cam;
+  RtbRenderOpts opts;
+  uint8_t* out = nullptr;
+  RtbStats st;
+  std::string err;              // empty = success
+  // renderAsync only
+  napi_deferred deferred = nullptr;
+  napi_async_work work = nullptr;
+  napi_ref out_ref = nullptr;   // keeps the Uint8ClampedArray (and its ArrayBuffer) alive until completion
+};
 
+void marshal(napi_env env, napi_value* argv, Job& J) {
+  {
     // ---- scene ------------------------------------------------------------------------------------
     napi_value objects = prop(env, argv[0], "objects");
     uint32_t n = 0;
     NAPI_OK(napi_get_array_length(env, objects, &n));
     if (n > (1u << 20)) throw Fail{"more than 2^20 spheres"};
-    std::vector<RtbSphere> spheres(n);
+    J.spheres.assign(n, RtbSphere{});
+    std::vector<RtbSphere>& spheres = J.spheres;
     for (uint32_t i = 0; i < n; i++) {
       napi_value o, m;
       NAPI_OK(napi_get_element(env, objects, i, &o));
@@ -168,8 +200,8 @@ napi_value Render(napi_env env, napi_callback_info info) {
       s.mtl.star_gain = num_prop(env, m, "star_gain", 1000);
       if (has(env, m, "checker_freq")) vec(env, m, "checker_freq", s.mtl.checker_freq, 2);
     }
-    std::vector<RtbTexture> textures;
-    std::vector<std::vector<uint8_t>> texel_store;
+    std::vector<RtbTexture>& textures = J.textures;
+    std::vector<std::vector<uint8_t>>& texel_store = J.texel_store;
     if (has(env, argv[0], "textures")) {
       napi_value ts = prop(env, argv[0], "textures");
       uint32_t nt = 0;
@@ -188,7 +220,7 @@ napi_value Render(napi_env env, napi_callback_info info) {
         textures[i].texels = texel_store[i].data();
       }
     }
-    RtbSceneDesc desc;
+    RtbSceneDesc& desc = J.desc;
     memset(&desc, 0, sizeof desc);
     desc.abi_version = RTB_ABI_VERSION;
     desc.n_spheres = (int32_t)n;
@@ -218,7 +250,7 @@ napi_value Render(napi_env env, napi_callback_info info) {
     desc.eps = num_prop(env, argv[0], "eps", 0.001);                        // main.js:430-445
 
     // ---- camera -----------------------------------------------------------------------------------
-    RtbCamera cam;
+    RtbCamera& cam = J.cam;
     memset(&cam, 0, sizeof cam);
     cam.width = (int32_t)num_prop(env, argv[1], "width", 0, true);
     cam.height = (int32_t)num_prop(env, argv[1], "height", 0, true);
@@ -232,7 +264,7 @@ napi_value Render(napi_env env, napi_callback_info info) {
     cam.camera_mode = (int32_t)num_prop(env, argv[1], "camera_mode", RTB_CAMERA_REFERENCE);
 
     // ---- options ----------------------------------------------------------------------------------
-    RtbRenderOpts o;
+    RtbRenderOpts& o = J.opts;
     rtb_default_opts(&o);
     o.segs = (int32_t)num_prop(env, argv[2], "segs", 8);                    // main.js:194
     o.spp_grid = (int32_t)num_prop(env, argv[2], "spp_grid", 1);
@@ -250,32 +282,117 @@ napi_value Render(napi_env env, napi_callback_info info) {
     NAPI_OK(napi_get_typedarray_info(env, argv[3], &ty, &len, &data, &ab, &off));
     if (ty != napi_uint8_clamped_array && ty != napi_uint8_array) throw Fail{"out must be a Uint8ClampedArray"};
     if (len < (size_t)cam.width * cam.height * 4) throw Fail{"out is smaller than width*height*4"};
+    J.out = static_cast<uint8_t*>(data);
 
-    if (rtb_init(-1) != RTB_OK) throw Fail{rtb_last_error()};
-    if (rtb_scene_create(&desc, &scene) != RTB_OK) throw Fail{rtb_last_error()};
-    RtbStats st;
-    if (rtb_render(scene, &cam, &o, (uint8_t*)data, &st) != RTB_OK) throw Fail{rtb_last_error()};
-    rtb_scene_destroy(scene);
-    scene = nullptr;
+  }
+}
 
-    napi_value res, v;
-    NAPI_OK(napi_create_object(env, &res));
-    NAPI_OK(napi_create_double(env, st.kernel_ms, &v)); NAPI_OK(napi_set_named_property(env, res, "kernel_ms", v));
-    NAPI_OK(napi_create_double(env, st.d2h_ms, &v)); NAPI_OK(napi_set_named_property(env, res, "d2h_ms", v));
-    NAPI_OK(napi_create_double(env, (double)st.nodes, &v)); NAPI_OK(napi_set_named_property(env, res, "nodes", v));
-    NAPI_OK(napi_create_double(env, (double)st.shadow_rays, &v)); NAPI_OK(napi_set_named_property(env, res, "shadow_rays", v));
-    NAPI_OK(napi_create_double(env, (double)st.launches, &v)); NAPI_OK(napi_set_named_property(env, res, "launches", v));
-    return res;
+// No Node-API call in here: this is what runs on the worker thread.
+void run(Job& J) {
+  rtb_scene_t scene = nullptr;
+  memset(&J.st, 0, sizeof J.st);
+  try {
+    if (rtb_init(-1) != RTB_OK) { J.err = rtb_last_error(); return; }
+    if (rtb_scene_create(&J.desc, &scene) != RTB_OK) { J.err = rtb_last_error(); return; }
+    if (rtb_render(scene, &J.cam, &J.opts, J.out, &J.st) != RTB_OK) J.err = rtb_last_error();
+  } catch (const std::exception& e) {
+    J.err = e.what();
+  } catch (...) {
+    J.err = "rtb200: unknown C++ exception";
+  }
+  if (scene) rtb_scene_destroy(scene);
+}
+
+napi_value result(napi_env env, const Job& J) {
+  napi_value res, v;
+  NAPI_OK(napi_create_object(env, &res));
+  NAPI_OK(napi_create_double(env, J.st.kernel_ms, &v)); NAPI_OK(napi_set_named_property(env, res, "kernel_ms", v));
+  NAPI_OK(napi_create_double(env, J.st.d2h_ms, &v)); NAPI_OK(napi_set_named_property(env, res, "d2h_ms", v));
+  NAPI_OK(napi_create_double(env, (double)J.st.nodes, &v)); NAPI_OK(napi_set_named_property(env, res, "nodes", v));
+  NAPI_OK(napi_create_double(env, (double)J.st.shadow_rays, &v)); NAPI_OK(napi_set_named_property(env, res, "shadow_rays", v));
+  NAPI_OK(napi_create_double(env, (double)J.st.launches, &v)); NAPI_OK(napi_set_named_property(env, res, "launches", v));
+  return res;
+}
+
+napi_value Render(napi_env env, napi_callback_info info) {
+  napi_value undef;
+  napi_get_undefined(env, &undef);
+  try {
+    size_t argc = 4;
+    napi_value argv[4];
+    NAPI_OK(napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+    if (argc < 4) throw Fail{"render(scene, camera, opts, out) takes 4 arguments"};
+    Job J;
+    marshal(env, argv, J);
+    run(J);
+    if (!J.err.empty()) throw Fail{J.err};
+    return result(env, J);
   } catch (const Fail& f) {
-    if (scene) rtb_scene_destroy(scene);
     napi_throw_error(env, nullptr, f.msg.c_str());          // JS `Error`; nothing crosses as a C++ exception
     return undef;
   } catch (const std::exception& e) {                       // std::bad_alloc / length_error of the staging vectors
-    if (scene) rtb_scene_destroy(scene);
     napi_throw_error(env, nullptr, e.what());
     return undef;
   } catch (...) {
-    if (scene) rtb_scene_destroy(scene);
+    napi_throw_error(env, nullptr, "rtb200: unknown C++ exception");
+    return undef;
+  }
+}
+
+// renderAsync(scene, camera, opts, out) -> Promise<stats>.  `out` must not be read or
+// resized by JavaScript until the promise settles; rows outside opts.y0..y1 are left untouched, so a page can
+// keep the reference's row-by-row cadence with one promise per band.
+void AsyncExecute(napi_env, void* data) { run(*static_cast<Job*>(data)); }
+
+void AsyncComplete(napi_env env, napi_status status, void* data) {
+  Job* J = static_cast<Job*>(data);
+  napi_value v = nullptr;
+  bool ok = status == napi_ok && J->err.empty();
+  if (ok) {
+    try { v = result(env, *J); } catch (...) { ok = false; J->err = "rtb200: could not build the result object"; }
+  }
+  if (ok) {
+    napi_resolve_deferred(env, J->deferred, v);
+  } else {
+    napi_value msg, err;
+    const std::string m = J->err.empty() ? std::string("rtb200: the async work was cancelled") : J->err;
+    napi_create_string_utf8(env, m.c_str(), NAPI_AUTO_LENGTH, &msg);
+    napi_create_error(env, nullptr, msg, &err);
+    napi_reject_deferred(env, J->deferred, err);
+  }
+  if (J->out_ref) napi_delete_reference(env, J->out_ref);
+  if (J->work) napi_delete_async_work(env, J->work);
+  delete J;
+}
+
+napi_value RenderAsync(napi_env env, napi_callback_info info) {
+  napi_value undef;
+  napi_get_undefined(env, &undef);
+  Job* J = nullptr;
+  try {
+    size_t argc = 4;
+    napi_value argv[4];
+    NAPI_OK(napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+    if (argc < 4) throw Fail{"renderAsync(scene, camera, opts, out) takes 4 arguments"};
+    J = new Job();
+    marshal(env, argv, *J);                                 // copies everything but the framebuffer
+    napi_value promise, name;
+    NAPI_OK(napi_create_reference(env, argv[3], 1, &J->out_ref));
+    NAPI_OK(napi_create_promise(env, &J->deferred, &promise));
+    NAPI_OK(napi_create_string_utf8(env, "rtb200.renderAsync", NAPI_AUTO_LENGTH, &name));
+    NAPI_OK(napi_create_async_work(env, nullptr, name, AsyncExecute, AsyncComplete, J, &J->work));
+    NAPI_OK(napi_queue_async_work(env, J->work));
+    return promise;                                         // J now belongs to AsyncComplete
+  } catch (const Fail& f) {
+    if (J) { if (J->out_ref) napi_delete_reference(env, J->out_ref); if (J->work) napi_delete_async_work(env, J->work); delete J; }
+    napi_throw_error(env, nullptr, f.msg.c_str());
+    return undef;
+  } catch (const std::exception& e) {
+    if (J) { if (J->out_ref) napi_delete_reference(env, J->out_ref); if (J->work) napi_delete_async_work(env, J->work); delete J; }
+    napi_throw_error(env, nullptr, e.what());
+    return undef;
+  } catch (...) {
+    if (J) { if (J->out_ref) napi_delete_reference(env, J->out_ref); if (J->work) napi_delete_async_work(env, J->work); delete J; }
     napi_throw_error(env, nullptr, "rtb200: unknown C++ exception");
     return undef;
   }
@@ -294,6 +411,8 @@ extern "C" __attribute__((visibility("default"))) napi_value napi_register_modul
   napi_value fn;
   if (napi_create_function(env, "render", NAPI_AUTO_LENGTH, Render, nullptr, &fn) == napi_ok)
     napi_set_named_property(env, exports, "render", fn);
+  if (napi_create_function(env, "renderAsync", NAPI_AUTO_LENGTH, RenderAsync, nullptr, &fn) == napi_ok)
+    napi_set_named_property(env, exports, "renderAsync", fn);
   if (napi_create_function(env, "version", NAPI_AUTO_LENGTH, Version, nullptr, &fn) == napi_ok)
     napi_set_named_property(env, exports, "version", fn);
   return exports;

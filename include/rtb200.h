@@ -304,6 +304,15 @@ int32_t rtb_stripe_local_rows(int32_t height, int32_t stripe_rows, int32_t strip
                               int32_t stripe_world);
 int32_t rtb_stripe_padded_rows(int32_t height, int32_t stripe_rows, int32_t stripe_world);
 
+/* Host-side inputs that fix the result, for hosts that bind this header directly (no device work):
+ *   rtb_look_at      main.js's closure-private lookAt(org, tgt, up) + the projection constants
+ *                    (main.js:92-105): fills origin, axisX/Y/Z, projW = W/2, projH = H/2, projD = projW/tan(30 deg).
+ *   rtb_sort_spheres objects.sort(...) of main.js:159-163 in place: ascending surface_area / distance to the
+ *                    camera origin (surface_area = 4*PI*r2), stable.  rtb_scene_create expects this order. */
+int rtb_look_at(const double org[3], const double tgt[3], const double up[3], int32_t width, int32_t height,
+                int32_t camera_mode, RtbCamera* out);
+int rtb_sort_spheres(RtbSphere* spheres, int32_t n, const double camera_origin[3]);
+
 /* Reference defaults (the literals of main.js) for the option/scene scalars. */
 void rtb_default_opts(RtbRenderOpts* opts);
 

@@ -136,3 +136,36 @@ def test_product_never_imports_the_oracle():
                 txt = open(os.path.join(dp, f), errors="replace").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
                 assert "liboracle" not in txt and "rt_oracle" not in txt, f
+
+
+def test_host_side_look_at_and_sort_match_the_reference_shaped_host_layer(rt, lib):
+    """rtb_look_at (main.js:92-105) and rtb_sort_spheres (main.js:159-163) are pure host code: bit-identical to the
+    Python mirror of main.js's lookAt / projection / objects.sort, which the golden frames of the unmodified
+    main.js pin (default camera: axisX = (-1,0,0), axisY = (0,1,0), axisZ = (0,0,-1))."""
+    A = rt._abi
+    out = A.RtbCamera()
+    assert lib.rtb_look_at(A.D3(0, 1.5, 10), A.D3(0, 1.5, 0), A.D3(0, 1, 0), 1280, 720, A.RTB_CAMERA_REFERENCE, C.byref(out)) == 0
+    assert list(out.axisX) == [-1.0, 0.0, 0.0] and list(out.axisY) == [0.0, 1.0, 0.0] and list(out.axisZ) == [0.0, 0.0, -1.0]
+    ref = rt.scenes.demo_camera(1280, 720).to_c()
+    for f in ("projW", "projH", "projD"):
+        assert getattr(out, f) == getattr(ref, f)
+    for cam in rt.scenes.orbit_cameras(640, 360, 24):      # rotated cameras
+        c = cam.to_c()
+        tgt = A.D3(0, 1.5, 0)
+        assert lib.rtb_look_at(c.origin, tgt, A.D3(0, 1, 0), 640, 360, A.RTB_CAMERA_BASIS, C.byref(out)) == 0
+        for f in ("origin", "axisX", "axisY", "axisZ"):
+            assert list(getattr(out, f)) == list(getattr(c, f)), f
+        assert out.camera_mode == A.RTB_CAMERA_BASIS
+    assert lib.rtb_look_at(A.D3(0, 0, 0), A.D3(0, 0, 1), A.D3(0, 1, 0), 0, 10, 0, C.byref(out)) == A.RTB_ERR_INVALID
+    # sort: the demo scene in SOURCE order and the 1024-sphere scene shuffled, against sortObjects
+    import random
+    for objs, origin in ((rt.scenes.demo_objects(), (0.0, 1.5, 10.0)), (rt.scenes.synth_objects(1024, 1024), (3.0, 2.0, -7.0))):
+        shuffled = list(objs)
+        random.Random(5).shuffle(shuffled)
+        want = list(shuffled)
+        rt.sortObjects(want, list(origin))
+        desc = rt.SceneDesc(shuffled)
+        assert lib.rtb_sort_spheres(desc.c.spheres, len(shuffled), A.D3(*origin)) == 0
+        got = [(tuple(desc.c.spheres[i].origin), desc.c.spheres[i].r2) for i in range(len(shuffled))]
+        assert got == [(tuple(float(c) for c in o.origin), o.r2) for o in want]
+    assert lib.rtb_sort_spheres(None, 3, A.D3(0, 0, 0)) == A.RTB_ERR_INVALID
