@@ -399,7 +399,13 @@ def main():
     host_seq = torch.empty((kb, H, W, 4), dtype=torch.uint8).pin_memory() if (rank == 0 and world <= 1) else None
     # N > 1: the frames land in ONE ring of host framebuffers in shared memory that every rank has mapped and
     # page-locked; each rank copies its own rows of every frame over its own PCIe link (SharedHostFrames)
-    ring = mg.SharedHostFrames(kb, H, W, rank, world) if world > 1 else None
+    ring, ring_note = None, ""
+    if world > 1:
+        try:
+            ring = mg.SharedHostFrames(kb, H, W, rank, world)       # collective: all ranks succeed or all raise
+        except RuntimeError as e:                                  # fall back: rank 0 reads every assembled frame back
+            ring_note = str(e)
+            host_seq = torch.empty((kb, H, W, 4), dtype=torch.uint8).pin_memory() if rank == 0 else None
     cams_c = (A.RtbCamera * kb)(*([cam_c] * kb))
 
     def e2e_sequence():
@@ -413,7 +419,13 @@ def main():
                 old = sr.r._h
                 sr.r._h = h
                 try:
-                    sr.redraw_sequence([cam] * kb, frames_in_flight=fif, host_frames=ring, **opts_kw)
+                    if ring is not None:
+                        sr.redraw_sequence([cam] * kb, frames_in_flight=fif, host_frames=ring, **opts_kw)
+                    else:
+                        def to_host(j, frame):
+                            if rank == 0:
+                                host_seq[j].copy_(frame, non_blocking=True)    # on the group's own stream
+                        sr.redraw_sequence([cam] * kb, on_frame=to_host, frames_in_flight=fif, **opts_kw)
                 finally:
                     sr.r._h = old
                 torch.cuda.synchronize()
@@ -528,9 +540,11 @@ def main():
                         f"{h2d_bytes} B) + " +
                         ("ONE rtb_render_batch call (every frame D2H into pinned host memory, under the kernels of the "
                          "next frames)" if world == 1 else
-                         "StripedRenderer.redraw_sequence into a ring of host framebuffers in shared, page-locked memory: "
-                         "every rank copies its own rows of every frame over its own PCIe link (rtb_stripe_rows_to_host), "
-                         "barrier at the end") + " + rtb_scene_destroy",
+                         ("StripedRenderer.redraw_sequence into a ring of host framebuffers in shared, page-locked memory: "
+                          "every rank copies its own rows of every frame over its own PCIe link (rtb_stripe_rows_to_host), "
+                          "barrier at the end" if not ring_note else
+                          f"StripedRenderer.redraw_sequence, rank 0 copies every assembled frame to pinned host memory ({ring_note})")
+                         ) + " + rtb_scene_destroy",
                 "single_frame": {"ms": round(single_ms, 4), "value": round(rays_per_frame / (single_ms * 1e-3) / 1e6, 2),
                                  "what": "one frame per call: rtb_scene_create + rtb_render into a pinned host buffer "
                                          "+ rtb_scene_destroy (nothing overlaps)"}},

@@ -126,30 +126,66 @@ class SharedHostFrames:
     Collective: every rank constructs it and every rank calls close()."""
 
     def __init__(self, n: int, height: int, width: int, rank: int, world: int):
+        import atexit
         import torch.distributed as dist
         from multiprocessing import resource_tracker, shared_memory
 
         self.n, self.H, self.W, self.rank, self.world = n, height, width, rank, world
         self.frame_bytes = height * width * 4
+        self.shm = None
         size = max(1, n * self.frame_bytes)
-        name = [None]
+        name, err = [None], None
         if rank == 0:
-            self.shm = shared_memory.SharedMemory(create=True, size=size)
-            name[0] = self.shm.name
+            try:
+                self.shm = shared_memory.SharedMemory(create=True, size=size)
+                name[0] = self.shm.name
+                atexit.register(self._unlink_at_exit)     # a crash before close() must not leave the segment behind
+            except Exception as e:                        # e.g. a /dev/shm too small for the ring
+                err = f"shared memory: {e}"
         if world > 1:
             dist.broadcast_object_list(name, src=0)
-        if rank != 0:
-            self.shm = shared_memory.SharedMemory(name=name[0], create=False)
-            try:                                          # attaching is not owning: only rank 0 unlinks
-                resource_tracker.unregister(self.shm._name, "shared_memory")
-            except Exception:
-                pass
-        self.frames = np.ndarray((n, height, width, 4), dtype=np.uint8, buffer=self.shm.buf)
-        self.base = self.frames.ctypes.data
         self.lib = A.load()
-        A.check(self.lib.rtb_host_register(C.c_void_p(self.base), size))
+        if name[0] is not None and rank != 0:
+            try:
+                self.shm = shared_memory.SharedMemory(name=name[0], create=False)
+                try:                                      # attaching is not owning: only rank 0 unlinks
+                    resource_tracker.unregister(self.shm._name, "shared_memory")
+                except Exception:
+                    pass
+            except Exception as e:
+                err = f"shared memory: {e}"
+        registered = False
+        if self.shm is not None and err is None:
+            self.frames = np.ndarray((n, height, width, 4), dtype=np.uint8, buffer=self.shm.buf)
+            self.base = self.frames.ctypes.data
+            rc = self.lib.rtb_host_register(C.c_void_p(self.base), size)
+            registered = rc == 0
+            if not registered:
+                err = "cudaHostRegister: " + self.lib.rtb_last_error().decode("utf-8", "replace")
+        # every rank takes the same decision
+        oks = [err is None and name[0] is not None]
         if world > 1:
-            dist.barrier()
+            gathered = [None] * world
+            dist.all_gather_object(gathered, (oks[0], err))
+            oks = [g[0] for g in gathered]
+            err = next((g[1] for g in gathered if g[1]), err)
+        if not all(oks):
+            if registered:
+                self.lib.rtb_host_unregister(C.c_void_p(self.base))
+            self.frames = None
+            if self.shm is not None:
+                self.shm.close()
+                if rank == 0:
+                    self.shm.unlink()
+                self.shm = None
+            raise RuntimeError(f"shared host frames unavailable ({err or 'a rank could not map the segment'})")
+
+    def _unlink_at_exit(self):
+        try:
+            if self.shm is not None and self.rank == 0:
+                self.shm.unlink()
+        except Exception:
+            pass
 
     def ptr(self, i: int) -> int:
         return self.base + (i % self.n) * self.frame_bytes
@@ -163,10 +199,10 @@ class SharedHostFrames:
         self.frames = None
         if self.world > 1:
             dist.barrier()
-        self.shm.close()
+        shm, self.shm = self.shm, None
+        shm.close()
         if self.rank == 0:
-            self.shm.unlink()
-        self.shm = None
+            shm.unlink()
 
 
 class StripedRenderer:

@@ -84,3 +84,61 @@ def test_single_process_degenerates_to_no_collective(rt):
     assert np.array_equal(mg.unstripe_numpy(g, 10, 4, 1), g[0])
     os.environ.pop("WORLD_SIZE", None)
     assert mg.init_distributed()[2] == 1
+
+
+def test_split_groups_partitions_a_sequence(rt):
+    mg = importlib.import_module("html5-canvas-raytracer_b200.multigpu")
+    assert mg.split_groups(20, 8) == [7, 7, 6] and mg.split_groups(20, 1) == [1] * 20
+    assert mg.split_groups(16, 8) == [8, 8] and mg.split_groups(3, 8) == [3] and mg.split_groups(0, 8) == []
+    for n in range(1, 60):
+        for g in range(1, 9):
+            s = mg.split_groups(n, g)
+            assert sum(s) == n and max(s) <= g and max(s) - min(s) <= 1 and len(s) == -(-n // g)
+    assert mg.default_group(1) == 1 and mg.default_group(4) == 4 and mg.default_group(16) == mg.MAX_GROUP
+
+
+def _ring_worker(rank, world, port, q):
+    """SharedHostFrames over gloo WITHOUT a GPU: the segment is created and mapped by every rank, page-locking it
+    fails (no device - there is no CPU fallback in the library), and every rank must reach the SAME verdict and
+    leave nothing behind in /dev/shm."""
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    mg = importlib.import_module("html5-canvas-raytracer_b200.multigpu")
+    mg.init_distributed(backend="gloo")
+    before = set(os.listdir("/dev/shm")) if os.path.isdir("/dev/shm") else set()
+    try:
+        ring = mg.SharedHostFrames(3, 8, 16, rank, world)
+        verdict = "ok"
+        ring.close()
+    except RuntimeError as e:
+        verdict = str(e)
+    dist.barrier()
+    after = set(os.listdir("/dev/shm")) if os.path.isdir("/dev/shm") else set()
+    q.put((rank, verdict, sorted(after - before)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shared_host_frames_fail_collectively_without_a_gpu(rt):
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("checks the no-device verdict")
+    except ImportError:
+        pytest.skip("torch missing")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ring_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=300) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, verdict, leaked in results:
+        assert "unavailable" in verdict and "cudaHostRegister" in verdict, (rank, verdict)
+        assert leaked == [], leaked
