@@ -339,3 +339,42 @@ def test_sequence_into_shared_host_frames(rt, synth):
             assert np.array_equal(ring.frames[i], refs[i]), i
     finally:
         ring.close()
+
+
+def test_frame_batch_renderer_collects_the_overflow_verdict(rt, synth):
+    """FrameBatchRenderer on the wavefront path (> 32 spheres): an asynchronous frame whose ray queues overflow is
+    re-rendered BEFORE the all-gather (advisor finding of round 1: the invalid frame used to be gathered silently,
+    or the ranks desynchronised)."""
+    import torch
+    mg = importlib.import_module("html5-canvas-raytracer_b200.multigpu")
+    W, H = 160, 90
+    cams = rt.scenes.orbit_cameras(W, H, 3)
+    kw = dict(segs=6, kernel=rt.RTB_KERNEL_WAVEFRONT)
+    refs = [synth.redraw(c, **kw) for c in cams]
+    os.environ["RTB_WF_CAP_NODES"] = str(W * 40)
+    os.environ["RTB_WF_NODES_PER_RAY"] = "1.05"            # bands sized too optimistically: the first attempt overflows
+    try:
+        with rt.Renderer(rt.scenes.synth_objects(160, 7)) as r:
+            fb = mg.FrameBatchRenderer(r, W, H, 0, 1)
+            for f in range(3):
+                out = fb.redraw_step(cams, f, **kw)
+                torch.cuda.synchronize()
+                assert np.array_equal(out[0].cpu().numpy(), refs[f]), f
+            assert r._lib.rtb_finish(r._h) == 0            # nothing left uncollected
+    finally:
+        del os.environ["RTB_WF_CAP_NODES"]
+        del os.environ["RTB_WF_NODES_PER_RAY"]
+
+
+def test_redraw_batch_validates_the_output_buffer(rt, demo):
+    cams = rt.scenes.orbit_cameras(64, 36, 3)
+    with pytest.raises(ValueError):
+        demo.redraw_batch(cams, out=np.zeros((2, 36, 64, 4), np.uint8))           # too small for 3 frames
+    with pytest.raises(ValueError):
+        demo.redraw_batch(cams, out=np.zeros((3, 36, 64, 4), np.float32))         # wrong dtype
+    with pytest.raises(ValueError):
+        demo.redraw_batch(cams, out=np.zeros((3, 36, 128, 4), np.uint8)[:, :, ::2])   # not contiguous
+    with pytest.raises(ValueError):
+        demo.redraw_batch([cams[0], rt.scenes.demo_camera(64, 40)])               # frames of different sizes
+    out = demo.redraw_batch(cams)
+    assert out.shape == (3, 36, 64, 4) and all(np.array_equal(out[i], demo.redraw(cams[i])) for i in range(3))
