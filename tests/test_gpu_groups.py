@@ -378,3 +378,32 @@ def test_redraw_batch_validates_the_output_buffer(rt, demo):
         demo.redraw_batch([cams[0], rt.scenes.demo_camera(64, 40)])               # frames of different sizes
     out = demo.redraw_batch(cams)
     assert out.shape == (3, 36, 64, 4) and all(np.array_equal(out[i], demo.redraw(cams[i])) for i in range(3))
+
+
+@pytest.mark.parametrize("lights", [
+    [],                                                              # no light: ambient / reflection only
+    [[5, 10, 5]],                                                    # one
+    [[5, 10, 5], [5, 10, 0], [-6, 8, 4]],                            # three: the second lq record (lights 2, 3)
+    [[5, 10, 5], [5, 10, 0], [-6, 8, 4], [0, 12, -6]],               # four = RTB_MAX_LIGHTS (main.js:283 lists 2 + 2)
+])
+def test_light_counts_against_the_oracle(rt, oracle, lights):
+    """0, 1, 3 and 4 lights: the light_intensity carry (main.js:284, declared once outside the loop) runs through
+    every facing light in order, through refractive occluders too (glass, bubble).  fp64 kernel bit-exact, fp32
+    kernels inside the gate, split and fused pipelines byte-identical."""
+    from conftest import FP32_WITHIN2, lsb_stats
+    W, H = 256, 144
+    cam = rt.scenes.demo_camera(W, H)
+    with rt.Renderer(rt.scenes.demo_objects(), lights=lights, light_intensity=50.0) as r:
+        ref, cnt = oracle.render(r.desc, cam, rt.make_opts(segs=8))
+        img64, st = r.redraw(cam, stats=True, segs=8, precision=rt.RTB_PRECISION_FP64)
+        assert np.array_equal(img64, ref) and st.shadow_rays == cnt["shadow_rays"]
+        frames = {}
+        for bits in ("7", "0"):
+            os.environ["RTB_WF_SPLIT"] = bits
+            try:
+                frames[bits] = r.redraw(cam, segs=8, kernel=rt.RTB_KERNEL_WAVEFRONT)
+            finally:
+                del os.environ["RTB_WF_SPLIT"]
+        assert np.array_equal(frames["7"], frames["0"])
+        assert lsb_stats(frames["7"], ref)["within2"] >= FP32_WITHIN2
+        assert lsb_stats(r.redraw(cam, segs=8, kernel=rt.RTB_KERNEL_PIXEL), ref)["within2"] >= FP32_WITHIN2
