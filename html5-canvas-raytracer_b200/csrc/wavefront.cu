@@ -1,18 +1,26 @@
 // wavefront.cu — fp32 THROUGHPUT path: the Whitted tree of main.js:220-337 evaluated
-// breadth-first over a whole row band instead of depth-first per pixel.
+// breadth-first over a whole row band — of one frame, or of a GROUP of up to 8 frames of a sequence at once
+// (rtb_render_device_group: level 1 holds the primary rays of every frame, all later work is shared) —
+// instead of depth-first per pixel.  One recursion level = a SWEEP kernel + a HIT kernel:
 //
-//   TRACE  level L : several rays per lane; closest-hit sweep over ALL spheres in array order from
-//                    shared memory (main.js:223-230), then the hit record, reflect/refract directions
-//                    (main.js:233-266), the sampler (main.js:320) and the occlusion-independent
-//                    part of the light loop (main.js:286-292, 306-313).  Live child rays and
-//                    shadow rays are compacted into queues with warp ballots (one atomic per warp).
-//   SHADOW light k : occluder sweep main.js:293-304 for every queued node, traced FROM the light so
-//                    that all rays of the launch share an origin.  The light_intensity
-//                    carry-over between lights (main.js:284, H1-b) is the queue hand-off
-//                    k -> next facing light.
+//   RAYGEN         : primary rays (main.js:186-193) in fp64 with each frame's own camera, rounded once.
+//   SWEEP  level L : several rays per lane; closest-hit sweep over ALL spheres in array order from shared
+//                    memory (main.js:223-230); writes key[node] = (t, sphere, flip).  Nothing else: every
+//                    resident warp is in the FMA-bound loop.
+//   HIT    level L : one thread per ray at high occupancy: the hit record, reflect/refract directions
+//                    (main.js:233-266), the sampler (main.js:320) and the occlusion-independent part of the
+//                    light loop (main.js:286-292, 306-313).  Live child rays and shadow-ray RECORDS are
+//                    compacted into queues with warp ballots, queue space reserved once per 256-node tile.
+//   SSWEEP light k : occluder sweep main.js:293-304 for every queued record, traced FROM the light so that
+//                    all rays of the launch share an origin.
+//   SPOST  light k : diffuse / specular sums (main.js:305-313) and the light_intensity carry-over between
+//                    lights (main.js:284, H1-b) = a new record in the queue of the next facing light.
 //   COMPOSE level L: post-order clamp-compose main.js:322-336, deepest level first; each child
 //                    writes its colour (scaled by the parent's albedo[3|4]) into its parent; level 1
 //                    averages sub-samples and stores RGBA8 as uint4 (4 pixels per thread).
+//
+// The round-1 FUSED forms (wf_trace_kernel = sweep + hit processing in one persistent kernel, wf_shadow_kernel =
+// sweep + post) are kept behind RTB_WF_SPLIT as the cross-check: both pipelines give byte-identical frames.
 //
 // The sweeps are written for the B200 SM as measured (tools/fp32_peak.cu, profiles/):
 //   * a warp-wide LDS.128 costs 4 LSU cycles even when all lanes read the same 16 bytes, so every
@@ -22,11 +30,12 @@
 //     half the issue slots of scalar FFMA and no 3-source register-bank conflicts
 //     (measured: scalar dot-shaped FFMA 76 % of peak, FFMA2 89 %);
 //   * the fast path never branches per test: the sign bit of each test value is funnel-shifted into
-//     a per-ray mask (one ALU-pipe instruction, off the FMA pipe) and a group of 16 spheres ends with
-//     a single branch; the slow path visits exactly the set bits (exact discriminant, sqrt, the
-//     0.001 window of main.js:429-439) and keeps the closest hit as a (t, index) key.
+//     a per-ray 32-bit mask (one ALU-pipe instruction, off the FMA pipe) and only after 32 spheres, when the
+//     masks are full, does the warp look at them (a single branch); the slow path visits exactly the set bits
+//     (exact discriminant from shared memory, sqrt, the 0.001 window of main.js:429-439) and keeps the closest
+//     hit as a (t, index) key.
 //
-// Every level is a persistent kernel that pulls fixed-size chunks from a device counter; bounds are
+// Every sweep is a persistent kernel that pulls fixed-size chunks from a device counter; bounds are
 // read from device counters too, so a band is a fixed launch sequence without host round trips.
 #include <algorithm>
 #include <cstdio>
