@@ -1429,9 +1429,26 @@ int wf_render(RtbScene_* s, const RtbCamera* cams, int n_frames, const DevFrameT
                            (const void*)wf_shadow_kernel, (const void*)wf_ssweep_kernel})
       RTB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
-  const int grid_p = grid_for((const void*)(split_p ? k_sweep_p : k_trace_p), smem);
-  const int grid_s = grid_for((const void*)(split_s ? k_sweep_s : k_trace_s), smem);
-  const int grid_l = grid_for(records ? (const void*)wf_ssweep_kernel : (const void*)wf_shadow_kernel, smem);
+  int grid_p = grid_for((const void*)(split_p ? k_sweep_p : k_trace_p), smem);
+  int grid_s = grid_for((const void*)(split_s ? k_sweep_s : k_trace_s), smem);
+  int grid_l = grid_for(records ? (const void*)wf_ssweep_kernel : (const void*)wf_shadow_kernel, smem);
+  // Three or more passes in flight: ONE persistent sweep CTA per SM instead of as many as fit.  A lone sweep
+  // loses ~3 % (the FMA pipe is almost saturated by 8 warps), but the registers it leaves free let the kernels
+  // of the OTHER passes in flight run beside it on the same SM - a second pass's sweep, or its HBM-bound hit /
+  // post / compose kernels, whose latency then hides under FMA work instead of owning the SMs between two
+  // sweeps (measured, 4K / 1024 spheres, 4 passes in flight: 8.06 -> 7.75 ms per frame; lone frame 8.5 -> 9.7 ms,
+  // which is why single frames keep the full grids).  RTB_WF_SWEEP_CTAS="p,s,l" (or one number) overrides.
+  {
+    int c[3] = {0, 0, 0};
+    if (async && g_rtb.frames_in_flight >= 3) c[0] = c[1] = c[2] = 1;
+    if (const char* e = getenv("RTB_WF_SWEEP_CTAS")) {
+      const int n = sscanf(e, "%d,%d,%d", &c[0], &c[1], &c[2]);
+      if (n == 1) c[1] = c[2] = c[0];
+    }
+    if (c[0] > 0) grid_p = std::min(grid_p, c[0] * g_rtb.sm_count);
+    if (c[1] > 0) grid_s = std::min(grid_s, c[1] * g_rtb.sm_count);
+    if (c[2] > 0) grid_l = std::min(grid_l, c[2] * g_rtb.sm_count);
+  }
   const int grid_h = split ? grid_for((const void*)k_hit_s, 0) : 0;
   const int grid_c = g_rtb.sm_count * 8;
 
