@@ -1273,6 +1273,24 @@ int rtb_finish_pending(int slot) {
   return RTB_OK;
 }
 
+// Kernel launch with a per-launch priority (cudaLaunchAttributePriority): with several passes in flight the short
+// HBM-bound kernels (raygen, hit, post, compose, resolve) sit on their pass's critical path between two long
+// sweeps; at high priority their blocks are dispatched before the pending sweep blocks of the other passes as
+// soon as an SM has room.  prio 0 = plain launch.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_k(void (*kernel)(KArgs...), int grid, size_t smem, cudaStream_t st, int prio, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(WF_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  if (prio != 0) {
+    attr[0].id = cudaLaunchAttributePriority;
+    attr[0].val.priority = prio;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+  }
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 int wf_render(RtbScene_* s, const RtbCamera* cams, int n_frames, const DevFrameT<float>& fr32, const RowMap& rm,
               uint8_t* const* d_outs, cudaStream_t st, RtbStats* stats, bool async, int slot) {
   if (stats) async = false;
@@ -1418,6 +1436,12 @@ int wf_render(RtbScene_* s, const RtbCamera* cams, int n_frames, const DevFrameT
     }
     return it->second * g_rtb.sm_count;
   };
+  // launch priorities (see launch_k): only with several passes in flight
+  static int prio_hi = 1, prio_lo = 1;
+  if (prio_hi == 1) { cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi); if (prio_hi == 1) prio_hi = 0; }
+  int use_prio = (async && g_rtb.frames_in_flight >= 3) ? 1 : 0;
+  if (const char* e = getenv("RTB_WF_PRIO")) use_prio = atoi(e);
+  const int prio_light = use_prio ? prio_hi : 0, prio_sweep = use_prio ? prio_lo : 0;
   typedef void (*LevelKernel)(WfParams, int);
   const LevelKernel k_trace_p = records ? wf_trace_kernel<true, true> : wf_trace_kernel<true, false>;
   const LevelKernel k_trace_s = records ? wf_trace_kernel<false, true> : wf_trace_kernel<false, false>;
@@ -1495,13 +1519,13 @@ int wf_render(RtbScene_* s, const RtbCamera* cams, int n_frames, const DevFrameT
       bands++;
       RTB_CUDA(cudaMemsetAsync(sl.wf.ctr, 0, sizeof(WfCounters), st));
       if ((rc = mark(T_START)) != RTB_OK) return rc;
-      wf_raygen_kernel<<<grid_c, WF_THREADS, 0, st>>>(P);
+      RTB_CUDA(launch_k(wf_raygen_kernel, grid_c, 0, st, prio_light, P));
       if (split_p) {
-        k_sweep_p<<<grid_p, WF_THREADS, smem, st>>>(P, 1);
-        k_hit_p<<<grid_h, WF_THREADS, 0, st>>>(P, 1);
+        RTB_CUDA(launch_k(k_sweep_p, grid_p, smem, st, prio_sweep, P, 1));
+        RTB_CUDA(launch_k(k_hit_p, grid_h, 0, st, prio_light, P, 1));
         launches += 3;
       } else {
-        k_trace_p<<<grid_p, WF_THREADS, smem, st>>>(P, 1);
+        RTB_CUDA(launch_k(k_trace_p, grid_p, smem, st, prio_sweep, P, 1));
         launches += 2;
       }
       if ((rc = mark(T_PRIMARY)) != RTB_OK) return rc;
@@ -1512,22 +1536,22 @@ int wf_render(RtbScene_* s, const RtbCamera* cams, int n_frames, const DevFrameT
         RTB_CUDA(cudaEventRecord(sl.ev_primary, st));
         RTB_CUDA(cudaStreamWaitEvent(sl.stream2, sl.ev_primary, 0));
         if (records) {
-          wf_ssweep_kernel<<<grid_l, WF_THREADS, smem, sl.stream2>>>(P, 0, 1);
-          wf_spost_kernel<<<grid_h, WF_THREADS, 0, sl.stream2>>>(P, 0, 1);
+          RTB_CUDA(launch_k(wf_ssweep_kernel, grid_l, smem, sl.stream2, prio_sweep, P, 0, 1));
+          RTB_CUDA(launch_k(wf_spost_kernel, grid_h, 0, sl.stream2, prio_light, P, 0, 1));
           launches += 2;
         } else {
-          wf_shadow_kernel<<<grid_l, WF_THREADS, smem, sl.stream2>>>(P, 0, 1);
+          RTB_CUDA(launch_k(wf_shadow_kernel, grid_l, smem, sl.stream2, prio_sweep, P, 0, 1));
           launches++;
         }
         RTB_CUDA(cudaEventRecord(sl.ev_early, sl.stream2));
       }
       for (int L = 2; L <= fr32.segs; L++) {
         if (split_s) {
-          k_sweep_s<<<grid_s, WF_THREADS, smem, st>>>(P, L);
-          k_hit_s<<<grid_h, WF_THREADS, 0, st>>>(P, L);
+          RTB_CUDA(launch_k(k_sweep_s, grid_s, smem, st, prio_sweep, P, L));
+          RTB_CUDA(launch_k(k_hit_s, grid_h, 0, st, prio_light, P, L));
           launches += 2;
         } else {
-          k_trace_s<<<grid_s, WF_THREADS, smem, st>>>(P, L);
+          RTB_CUDA(launch_k(k_trace_s, grid_s, smem, st, prio_sweep, P, L));
           launches++;
         }
       }
@@ -1540,20 +1564,20 @@ int wf_render(RtbScene_* s, const RtbCamera* cams, int n_frames, const DevFrameT
       for (int k = 0; k < s->n_lights; k++) {
         const int phase = (k == 0 && overlap) ? 2 : 0;
         if (records) {
-          wf_ssweep_kernel<<<grid_l, WF_THREADS, smem, st>>>(P, k, phase);
-          wf_spost_kernel<<<grid_h, WF_THREADS, 0, st>>>(P, k, phase);
+          RTB_CUDA(launch_k(wf_ssweep_kernel, grid_l, smem, st, prio_sweep, P, k, phase));
+          RTB_CUDA(launch_k(wf_spost_kernel, grid_h, 0, st, prio_light, P, k, phase));
           launches += 2;
         } else {
-          wf_shadow_kernel<<<grid_l, WF_THREADS, smem, st>>>(P, k, phase);
+          RTB_CUDA(launch_k(wf_shadow_kernel, grid_l, smem, st, prio_sweep, P, k, phase));
           launches++;
         }
       }
       if ((rc = mark(T_SHADOW)) != RTB_OK) return rc;
       for (int L = fr32.segs; L >= 2; L--) {
-        wf_compose_kernel<<<grid_c, WF_THREADS, 0, st>>>(P, L);
+        RTB_CUDA(launch_k(wf_compose_kernel, grid_c, 0, st, prio_light, P, L));
         launches++;
       }
-      wf_resolve_kernel<<<grid_c, WF_THREADS, 0, st>>>(P);
+      RTB_CUDA(launch_k(wf_resolve_kernel, grid_c, 0, st, prio_light, P));
       launches++;
       if ((rc = mark(T_COMPOSE)) != RTB_OK) return rc;
       RTB_CUDA(cudaGetLastError());
