@@ -227,7 +227,7 @@ def main():
     ap.add_argument("--frames-in-flight", type=int, default=0,
                     help="wavefront passes the sequence keeps in flight (0 = the host layer's default)")
     ap.add_argument("--group", type=int, default=0,
-                    help="frames per wavefront pass in sequence mode (0 = the host layer's default: the GPU count)")
+                    help="frames per wavefront pass in sequence mode (0 = the host layer's default: multigpu.default_group)")
     ap.add_argument("--config", default=CONFIG,
                     choices=["c3_synth1024_4k", "c2_demo_1080p_segs5", "c4_demo_4k_16spp"],
                     help="BASELINE.json config; the default (configs[2]) is the one the metric is quoted on")

@@ -30,9 +30,10 @@ MAX_IN_FLIGHT = 8            # = RTB_MAX_IN_FLIGHT of the library: wavefront pas
 MAX_GROUP = A.RTB_MAX_GROUP  # frames one wavefront pass renders together (rtb_render_device_group)
 DEFAULT_IN_FLIGHT = 4        # passes redraw_sequence keeps in flight on one GPU (measured, 4K frames on one B200:
                              # 9.58 ms per frame with one in flight, 9.16 with four)
-DEFAULT_IN_FLIGHT_MULTI = 3  # ... with world > 1, where a pass is a GROUP of `world` frames: each rank renders 1/world
-                             # of every frame, so a group is a whole frame's worth of rays per pass; the second pass in
-                             # flight hides the exchange and fills the tails of the first
+DEFAULT_IN_FLIGHT_MULTI = 6  # ... with world > 1, where a pass is a GROUP of frames (default_group): measured with 20-frame
+                             # 4K sequences, ms per frame, (group, passes in flight): 2 GPUs (2,3) 4.07, (2,6) 3.92, (1,6) 3.98;
+                             # 4 GPUs (4,3) 2.07, (4,6) 2.05, (2,6) 2.03; 8 GPUs (8,3) 1.058, (4,6) 1.068 [end to end 1.34 vs
+                             # 1.23: smaller groups complete earlier, their host copies overlap the next passes], (2,8) 1.078
 MAX_REPEATS = 64             # frames re-rendered because of ray-queue overflows before giving up (as rtb_render_batch)
 
 
@@ -41,9 +42,12 @@ def default_in_flight(world: int) -> int:
 
 
 def default_group(world: int) -> int:
-    """Frames per wavefront pass in sequence mode: with the rows of a frame dealt over `world` GPUs, `world`
-    frames per pass give every kernel launch the size it has on a single GPU."""
-    return max(1, min(world, MAX_GROUP))
+    """Frames per wavefront pass in sequence mode.  With the rows of a frame dealt over `world` GPUs, `world`
+    frames per pass give every kernel launch the size it has on a single GPU; half of that (from 4 GPUs on) with
+    six passes in flight measured as fast or faster and delivers frames earlier (see DEFAULT_IN_FLIGHT_MULTI)."""
+    if world <= 2:
+        return max(1, world)
+    return max(1, min(world // 2, MAX_GROUP))
 
 
 def split_groups(n: int, group: int) -> List[int]:

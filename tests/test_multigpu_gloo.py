@@ -94,7 +94,7 @@ def test_split_groups_partitions_a_sequence(rt):
         for g in range(1, 9):
             s = mg.split_groups(n, g)
             assert sum(s) == n and max(s) <= g and max(s) - min(s) <= 1 and len(s) == -(-n // g)
-    assert mg.default_group(1) == 1 and mg.default_group(4) == 4 and mg.default_group(16) == mg.MAX_GROUP
+    assert [mg.default_group(w) for w in (1, 2, 3, 4, 8, 16, 32)] == [1, 2, 1, 2, 4, 8, mg.MAX_GROUP]
 
 
 def _ring_worker(rank, world, port, q):

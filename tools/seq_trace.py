@@ -19,7 +19,7 @@ cam = rt.scenes.demo_camera(W, H)
 kw = dict(segs=8, kernel=rt.RTB_KERNEL_AUTO)
 out = []
 with rt.Renderer(rt.scenes.synth_objects(1024, 1024), device=local_rank) as r:
-    sr = mg.StripedRenderer(r, W, H, rank, world, group=grp, slots=max(fif, 3) if world > 1 else 0)
+    sr = mg.StripedRenderer(r, W, H, rank, world, group=grp, slots=max(fif or mg.default_in_flight(world), 3) if world > 1 else 0)
     sr.redraw_sequence([cam] * (4 * sr.G), frames_in_flight=fif, **kw)
     for rep in range(3):
         if world > 1:
