@@ -6,7 +6,9 @@
     rows PACKED into a [padded_rows, W, 4] buffer; the exchange is either the library's scatter kernel
     over NVLink peer memory (rows stored straight into every rank's framebuffer) or one
     `all_gather_into_tensor` (NCCL) plus a de-interleave kernel.  It exists only when world > 1.
-    Sequences keep several frames in flight per GPU (redraw_sequence).
+    Sequences (redraw_sequence) are rendered in GROUPS of frames per wavefront pass (rtb_render_device_group),
+    several passes in flight per GPU; with SharedHostFrames every rank also copies its own rows of every frame
+    into one ring of host framebuffers in shared, page-locked memory (the box's PCIe links in parallel).
   * frame batches (config 5): frame f -> rank f % world; the rendered frames are all-gathered.
 
 torch is used for process-group plumbing and device buffers only; all rendering goes through the

@@ -169,3 +169,29 @@ def test_host_side_look_at_and_sort_match_the_reference_shaped_host_layer(rt, li
         got = [(tuple(desc.c.spheres[i].origin), desc.c.spheres[i].r2) for i in range(len(shuffled))]
         assert got == [(tuple(float(c) for c in o.origin), o.r2) for o in want]
     assert lib.rtb_sort_spheres(None, 3, A.D3(0, 0, 0)) == A.RTB_ERR_INVALID
+
+
+def test_bench_reference_arm_prints_the_contract_line_with_all_host_threads():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm): ONE JSON line with the contract's
+    keys, the workload `config` the GPU arm prints too, and every host thread at work even under torchrun's
+    OMP_NUM_THREADS=1 (round 1: the N > 1 reference runs silently used one thread)."""
+    import json
+    env = dict(os.environ, OMP_NUM_THREADS="1", RANK="0", WORLD_SIZE="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0", "--gpus", "2"], capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+              "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["metric"] == "Mrays/s" and d["n_gpus"] == 2 and d["value"] > 0
+    assert d["config"]["workload"] == "c3_synth1024_4k" and d["config"]["n_spheres"] == 1024
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
+    assert d["e2e"] == {"value": d["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # every other rank of a torchrun launch exits 0 without work and without output
+    env["RANK"] = "1"
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0", "--gpus", "2"], capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0 and out.stdout.strip() == ""

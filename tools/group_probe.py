@@ -31,8 +31,6 @@ with rt.Renderer(objs) as r:
             t0 = time.perf_counter()
             for i, n in enumerate(sizes):
                 s = i % D
-                if G == 1:
-                    st = torch.cuda.Stream() if False else streams[s % 4]
                 with torch.cuda.stream(streams[s % 4]):
                     r.redraw_device_group([cam] * n, o, [dev[s % 4, b].data_ptr() for b in range(n)],
                                           streams[s % 4].cuda_stream)
