@@ -465,3 +465,23 @@ def test_star_stream_replay_matches_unmodified_main_js(rt, oracle, demo):
     with pytest.raises(rt.RtbError) as e:
         demo.redraw(cam2, precision=rt.RTB_PRECISION_FP64, star_mode=rt.RTB_STARS_STREAM, star_stream=big, y0=0, y1=10)
     assert e.value.code == rt._abi.RTB_ERR_UNSUPPORTED
+
+
+def test_gpu_kernels_against_the_unmodified_main_js_frames(rt, demo):
+    """The committed framebuffers of the UNMODIFIED main.js (tests/golden/mainjs_demo_*.npz, oracle/gen_golden.py)
+    are the reference itself: the fp64 validation kernel and the fp32 kernels are held to the north star's gates
+    against THEM directly, not only against the C restatement (which reproduces them bit-exactly)."""
+    golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    files = sorted(f for f in os.listdir(golden) if f.startswith("mainjs_demo_") and f.endswith(".npz") and "stars" not in f)
+    assert len(files) >= 4
+    for f in files:
+        gold = np.load(os.path.join(golden, f))["rgba"]
+        h, w = gold.shape[:2]
+        cam = rt.scenes.demo_camera(w, h)
+        s64 = lsb_stats(demo.redraw(cam, segs=8, precision=rt.RTB_PRECISION_FP64), gold)
+        assert s64["within1"] >= FP64_WITHIN1 and s64["psnr"] >= FP64_PSNR_DB and s64["alpha_ok"], (f, s64)
+        if w * h >= 160 * 90:       # the fp32 gate is a fraction of pixels: meaningful from ~10^4 pixels on
+            for kernel in (rt.RTB_KERNEL_WAVEFRONT, rt.RTB_KERNEL_PIXEL):
+                s32 = lsb_stats(demo.redraw(cam, segs=8, kernel=kernel), gold)
+                assert s32["within2"] >= FP32_WITHIN2 and s32["psnr"] >= FP32_PSNR_DB, (f, kernel, s32)
+        print(f, "fp64 exact", s64["exact"])
