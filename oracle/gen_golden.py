@@ -54,7 +54,11 @@ def star_stream(n):
     return ((k * np.uint64(2654435761)) % np.uint64(4294967296)).astype(np.float64) / 4294967296.0 * 0.004
 
 
-def run_main_js(width, height, main_js_path=os.path.join(REFERENCE, "main.js"), verbose=False, stars=False):
+def run_main_js(width, height, main_js_path=os.path.join(REFERENCE, "main.js"), verbose=False, stars=False,
+                module_only=False):
+    """module_only: evaluate the module (its top-level function declarations become globals of the interpreter)
+    and return the Interpreter WITHOUT firing body.onload - for harness-driven calls of the reference's own
+    functions (gen_golden_rays.py)."""
     png = importlib.import_module("html5-canvas-raytracer_b200.png")
     draws = [0]
 
@@ -142,6 +146,8 @@ def run_main_js(width, height, main_js_path=os.path.join(REFERENCE, "main.js"), 
     src = open(main_js_path).read()
     t0 = time.time()
     it.run(src)                                     # module evaluation: IIFE hooks console.log, sets body.onload
+    if module_only:
+        return it
     onload = body.props["onload"]
     call(onload, body, [])                          # document.body.onload = main  (main.js:17)
     n = it.drain_timers()
