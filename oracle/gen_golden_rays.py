@@ -94,6 +94,31 @@ def main():
                                         "unmodified main.js build 741, evaluated under oracle/minijs (gen_golden_rays.py)"))
     print("wrote", path, res.shape, "non-trivial colours:", int((res.max(axis=2) > 0).sum()))
 
+    # sampleTexture (main.js:343-351: nearest texel, ceil(u*w) - 1 addressing, no wrap) and checkerTexture
+    # (main.js:353-373) themselves: a 7 x 5 texture with distinct texels, (u, v) on a grid that includes 0, 1,
+    # exact texel boundaries and values just beside them
+    tw, th = 7, 5
+    texels = rng.integers(0, 256, tw * th * 4)
+    us = sorted(set([0.0, 1.0, 1e-12, 1 - 1e-12] + [i / tw for i in range(tw + 1)] + [i / tw + 1e-9 for i in range(tw)] +
+                    list(rng.random(12))))
+    vs = sorted(set([0.0, 1.0] + [i / th for i in range(th + 1)] + [i / th - 1e-9 for i in range(1, th + 1)] + list(rng.random(8))))
+    snippet = ["const t2 = createTexture();", "t2.width = %d; t2.height = %d;" % (tw, th),
+               "t2.texels = [%s];" % ",".join(str(int(v)) for v in texels), "const so = [];",
+               "const us = [%s]; const vs = [%s];" % (",".join(js_num(u) for u in us), ",".join(js_num(v) for v in vs)),
+               "for (let j = 0; j < vs.length; j++) { for (let i = 0; i < us.length; i++) { so.push(sampleTexture(t2, us[i], vs[j])); } }",
+               "const ck = createTexture();", "checkerTexture(ck, 6, 4, [0,1,1], [1,0,1]);"]
+    it.run("\n".join(snippet))
+    so = it.globals.vars["so"]
+    samp = np.array([[to_number(c) for c in v.items] for v in so.items], np.float64).reshape(len(vs), len(us), 3)
+    ck = it.globals.vars["ck"]
+    ck_tex = np.array([to_number(c) for c in ck.props["texels"].items], np.float64)
+    path2 = os.path.join(ROOT, "tests", "golden", "mainjs_sampler_vectors.npz")
+    np.savez_compressed(path2, tex_w=np.array(tw), tex_h=np.array(th), texels=texels.astype(np.uint8), us=np.array(us),
+                        vs=np.array(vs), rgb=samp, checker_w=np.array(6), checker_h=np.array(4),
+                        checker_c0=np.array([0.0, 1.0, 1.0]), checker_c1=np.array([1.0, 0.0, 1.0]), checker_texels=ck_tex,
+                        source=np.array("sampleTexture / checkerTexture of the unmodified main.js build 741 under oracle/minijs"))
+    print("wrote", path2, samp.shape, ck_tex.shape)
+
 
 if __name__ == "__main__":
     main()

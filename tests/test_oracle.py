@@ -358,3 +358,23 @@ def test_oracle_matches_the_references_own_tracer_on_a_non_demo_scene(rt, oracle
     assert lit > 900 and tir > 0                           # the vectors do exercise shading and total internal reflection
     # deeper recursion changes what reflective / glass spheres return: the depth axis is not degenerate
     assert np.abs(gold[0] - gold[3]).max() > 0.05 and np.abs(gold[2] - gold[3]).max() > 0
+
+
+def test_samplers_match_the_references_own_functions(rt, oracle):
+    """tests/golden/mainjs_sampler_vectors.npz: the reference's sampleTexture (main.js:343-351) on a 7 x 5 texture
+    over a (u, v) grid with 0, 1, exact texel boundaries and their neighbours, and its checkerTexture
+    (main.js:353-373) - against the restatement's sampler and the host layer's checkerTexture."""
+    import ctypes as C
+    z = np.load(os.path.join(GOLDEN, "mainjs_sampler_vectors.npz"))
+    tw, th = int(z["tex_w"]), int(z["tex_h"])
+    texels = np.ascontiguousarray(z["texels"], np.uint8)
+    t = rt._abi.RtbTexture(tw, th, texels.ctypes.data_as(C.POINTER(C.c_uint8)))
+    L = oracle.lib()
+    out = rt._abi.D3()
+    for j, v in enumerate(z["vs"]):
+        for i, u in enumerate(z["us"]):
+            L.oracle_sample_texture(C.byref(t), float(u), float(v), out)
+            assert list(out) == list(z["rgb"][j, i]), (u, v)
+    ck = rt.createTexture()
+    rt.checkerTexture(ck, int(z["checker_w"]), int(z["checker_h"]), list(z["checker_c0"]), list(z["checker_c1"]))
+    assert np.array_equal(np.asarray(ck.texels, np.float64), z["checker_texels"])
