@@ -71,5 +71,25 @@ int rtb_sort_spheres(RtbSphere* spheres, int32_t n, const double camera_origin[3
   return RTB_OK;
 }
 
+// Diagnostics (host only): the packed sweep tables the wavefront kernels stage in shared memory, as built by
+// wf_make_table / wf_make_geom_table for `origin` - so that their safety margins ("fp32 rounding can only ADD
+// candidates, never lose a true hit") can be checked on the CPU against float64 for arbitrary scenes
+// (tests/test_sweep_tables.py).  Layout per sphere PAIR p: tab[8p..8p+7] = x0 x1 y0 y1 z0 z1 w0 w1.
+// Buffers hold rtb_debug_table_pad(n_spheres) * 4 floats each; exact = (Lx, Ly, Lz, |L|^2 - r2) per sphere.
+int32_t rtb_debug_table_pad(int32_t n_spheres) { return wf_pad(n_spheres > 0 ? n_spheres : 1); }
+
+int rtb_debug_sweep_tables(const RtbSceneDesc* d, const double origin[3], float* origin_tab, float* origin_exact,
+                           float* general_tab) {
+  if (!d || !origin || !origin_tab || !origin_exact || !general_tab || d->n_spheres < 0 ||
+      (d->n_spheres > 0 && !d->spheres)) {
+    rtb_set_error("bad table arguments");
+    return RTB_ERR_INVALID;
+  }
+  const int n = d->n_spheres, np = wf_pad(n > 0 ? n : 1);
+  wf_make_table(d->spheres, n, np, origin, reinterpret_cast<float4*>(origin_tab), reinterpret_cast<float4*>(origin_exact));
+  wf_make_geom_table(d->spheres, n, np, reinterpret_cast<float4*>(general_tab));
+  return RTB_OK;
+}
+
 }  // extern "C"
 #pragma GCC visibility pop

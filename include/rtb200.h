@@ -313,6 +313,14 @@ int rtb_look_at(const double org[3], const double tgt[3], const double up[3], in
                 int32_t camera_mode, RtbCamera* out);
 int rtb_sort_spheres(RtbSphere* spheres, int32_t n, const double camera_origin[3]);
 
+/* Diagnostics, host only: the packed sweep tables of the wavefront kernels for rays leaving `origin` (camera or
+ * light) and for general rays, exactly as the library builds them - lets a test check their safety margins
+ * against float64 on the CPU.  Per sphere pair p: tab[8p..8p+7] = x0 x1 y0 y1 z0 z1 w0 w1; every buffer holds
+ * rtb_debug_table_pad(n_spheres) * 4 floats. */
+int32_t rtb_debug_table_pad(int32_t n_spheres);
+int rtb_debug_sweep_tables(const RtbSceneDesc* desc, const double origin[3], float* origin_tab, float* origin_exact,
+                           float* general_tab);
+
 /* Reference defaults (the literals of main.js) for the option/scene scalars. */
 void rtb_default_opts(RtbRenderOpts* opts);
 
