@@ -124,6 +124,7 @@ EXPORTS = [
     "rtb_stripe_padded_rows", "rtb_default_opts", "rtb_last_error", "rtb_version",
     "rtb_abi_version", "rtb_device_info", "rtb_clock_probe", "rtb_stripe_rows_to_host", "rtb_host_register",
     "rtb_host_unregister", "rtb_look_at", "rtb_sort_spheres", "rtb_debug_table_pad", "rtb_debug_sweep_tables",
+    "rtb_decode_png",
 ]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -198,6 +199,8 @@ def load() -> C.CDLL:
     lib.rtb_look_at.argtypes = [D3, D3, D3, C.c_int32, C.c_int32, C.c_int32, C.POINTER(RtbCamera)]
     lib.rtb_look_at.restype = C.c_int
     lib.rtb_sort_spheres.argtypes = [C.POINTER(RtbSphere), C.c_int32, D3]; lib.rtb_sort_spheres.restype = C.c_int
+    lib.rtb_decode_png.argtypes = [vp, C.c_uint64, C.POINTER(C.c_int32), C.POINTER(C.c_int32), vp, C.c_uint64]
+    lib.rtb_decode_png.restype = C.c_int
     lib.rtb_debug_table_pad.argtypes = [C.c_int32]; lib.rtb_debug_table_pad.restype = C.c_int32
     lib.rtb_debug_sweep_tables.argtypes = [C.POINTER(RtbSceneDesc), D3, vp, vp, vp]; lib.rtb_debug_sweep_tables.restype = C.c_int
     lib.rtb_clock_probe.argtypes = [vp, C.c_int32, vp]; lib.rtb_clock_probe.restype = C.c_int

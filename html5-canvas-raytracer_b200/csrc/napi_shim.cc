@@ -3,6 +3,7 @@
 //   const rtb = require('./rtb200.node');
 //   rtb.render(scene, camera, opts, colorbuf.data);      // fills the Uint8ClampedArray in place
 //   await rtb.renderAsync(scene, camera, opts, colorbuf.data);   // same on a worker thread, returns a Promise
+//   const tex = rtb.decodeTexture(fs.readFileSync('earth.png'));  // loadTexture without a canvas (main.js:375-395)
 //
 // It replaces the pixel loops of main.js's redraw()/spanish() (main.js:180-199): JavaScript hands over
 // the same scene description main() builds (main.js:85-163) and gets back the bytes it would have
@@ -73,6 +74,10 @@ napi_status napi_create_async_work(napi_env, napi_value async_resource, napi_val
 napi_status napi_queue_async_work(napi_env, napi_async_work work);
 napi_status napi_delete_async_work(napi_env, napi_async_work work);
 napi_status napi_create_reference(napi_env, napi_value value, uint32_t initial_refcount, napi_ref* result);
+// decodeTexture: a fresh Uint8ClampedArray for the texels
+napi_status napi_create_arraybuffer(napi_env, size_t byte_length, void** data, napi_value* result);
+napi_status napi_create_typedarray(napi_env, napi_typedarray_type type, size_t length, napi_value arraybuffer,
+                                   size_t byte_offset, napi_value* result);
 napi_status napi_delete_reference(napi_env, napi_ref ref);
 }
 #define NAPI_AUTO_LENGTH SIZE_MAX
@@ -398,6 +403,48 @@ napi_value RenderAsync(napi_env env, napi_callback_info info) {
   }
 }
 
+// decodeTexture(pngBytes: Uint8Array | Buffer) -> {width, height, texels: Uint8ClampedArray, loaded: 1}: the object
+// loadTexture leaves behind once img.onload has run (main.js:385-393), for hosts without Image / canvas.
+napi_value DecodeTexture(napi_env env, napi_callback_info info) {
+  napi_value undef;
+  napi_get_undefined(env, &undef);
+  try {
+    size_t argc = 1;
+    napi_value argv[1];
+    NAPI_OK(napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+    if (argc < 1) throw Fail{"decodeTexture(pngBytes) takes 1 argument"};
+    bool typed = false;
+    NAPI_OK(napi_is_typedarray(env, argv[0], &typed));
+    if (!typed) throw Fail{"decodeTexture: expected a Uint8Array / Buffer of PNG bytes"};
+    napi_typedarray_type ty; size_t len = 0; void* data = nullptr; napi_value ab; size_t off = 0;
+    NAPI_OK(napi_get_typedarray_info(env, argv[0], &ty, &len, &data, &ab, &off));
+    if (ty != napi_uint8_array && ty != napi_uint8_clamped_array) throw Fail{"decodeTexture: expected a Uint8Array / Buffer"};
+    int32_t w = 0, h = 0;
+    if (rtb_decode_png((const uint8_t*)data, len, &w, &h, nullptr, 0) != RTB_OK) throw Fail{rtb_last_error()};
+    const size_t bytes = (size_t)w * (size_t)h * 4;
+    void* texels = nullptr;
+    napi_value buf, arr, res, v;
+    NAPI_OK(napi_create_arraybuffer(env, bytes, &texels, &buf));
+    if (rtb_decode_png((const uint8_t*)data, len, &w, &h, (uint8_t*)texels, bytes) != RTB_OK) throw Fail{rtb_last_error()};
+    NAPI_OK(napi_create_typedarray(env, napi_uint8_clamped_array, bytes, buf, 0, &arr));
+    NAPI_OK(napi_create_object(env, &res));
+    NAPI_OK(napi_create_double(env, w, &v)); NAPI_OK(napi_set_named_property(env, res, "width", v));
+    NAPI_OK(napi_create_double(env, h, &v)); NAPI_OK(napi_set_named_property(env, res, "height", v));
+    NAPI_OK(napi_create_double(env, 1, &v)); NAPI_OK(napi_set_named_property(env, res, "loaded", v));
+    NAPI_OK(napi_set_named_property(env, res, "texels", arr));
+    return res;
+  } catch (const Fail& f) {
+    napi_throw_error(env, nullptr, f.msg.c_str());
+    return undef;
+  } catch (const std::exception& e) {
+    napi_throw_error(env, nullptr, e.what());
+    return undef;
+  } catch (...) {
+    napi_throw_error(env, nullptr, "rtb200: unknown C++ exception");
+    return undef;
+  }
+}
+
 napi_value Version(napi_env env, napi_callback_info) {
   napi_value v;
   napi_create_string_utf8(env, rtb_version(), NAPI_AUTO_LENGTH, &v);
@@ -413,6 +460,8 @@ extern "C" __attribute__((visibility("default"))) napi_value napi_register_modul
     napi_set_named_property(env, exports, "render", fn);
   if (napi_create_function(env, "renderAsync", NAPI_AUTO_LENGTH, RenderAsync, nullptr, &fn) == napi_ok)
     napi_set_named_property(env, exports, "renderAsync", fn);
+  if (napi_create_function(env, "decodeTexture", NAPI_AUTO_LENGTH, DecodeTexture, nullptr, &fn) == napi_ok)
+    napi_set_named_property(env, exports, "decodeTexture", fn);
   if (napi_create_function(env, "version", NAPI_AUTO_LENGTH, Version, nullptr, &fn) == napi_ok)
     napi_set_named_property(env, exports, "version", fn);
   return exports;

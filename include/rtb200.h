@@ -313,6 +313,14 @@ int rtb_look_at(const double org[3], const double tgt[3], const double up[3], in
                 int32_t camera_mode, RtbCamera* out);
 int rtb_sort_spheres(RtbSphere* spheres, int32_t n, const double camera_origin[3]);
 
+/* loadTexture without the browser (main.js:375-395: Image -> offscreen canvas -> getImageData), host only: PNG
+ * bytes -> the RGBA8 texels an RtbTexture wants.  Call once with out_rgba8 == NULL for the size, then with a
+ * buffer of width*height*4 bytes.  Non-interlaced 8-bit greyscale / RGB / palette (+ tRNS) / grey+alpha / RGBA;
+ * the reference's earth.png / mars.png are 8-bit palette images (PLTE only).  zlib is bound at run time
+ * (libz.so.1); without it RTB_ERR_UNSUPPORTED. */
+int rtb_decode_png(const uint8_t* png, uint64_t len, int32_t* width, int32_t* height, uint8_t* out_rgba8,
+                   uint64_t out_capacity);
+
 /* Diagnostics, host only: the packed sweep tables of the wavefront kernels for rays leaving `origin` (camera or
  * light) and for general rays, exactly as the library builds them - lets a test check their safety margins
  * against float64 on the CPU.  Per sphere pair p: tab[8p..8p+7] = x0 x1 y0 y1 z0 z1 w0 w1; every buffer holds

@@ -5,6 +5,7 @@
 // they bind to the `node` executable in production.  Python drives it through the mock_* helpers (ctypes).
 #include <dlfcn.h>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -160,6 +161,16 @@ napi_status napi_queue_async_work(napi_env env, napi_async_work w) {
 }
 napi_status napi_delete_async_work(napi_env, napi_async_work w) { w->deleted = true; return napi_ok; }
 napi_status napi_create_reference(napi_env env, napi_value v, uint32_t, napi_ref* r) { *r = new napi_ref__{v}; env->live_refs++; return napi_ok; }
+napi_status napi_create_arraybuffer(napi_env, size_t n, void** data, napi_value* r) {
+  *r = mk(K_TYPED); (*r)->ta_type = -1; (*r)->len = n; (*r)->data = n ? calloc(n, 1) : nullptr;   // never freed: no GC here
+  if (data) *data = (*r)->data;
+  return napi_ok;
+}
+napi_status napi_create_typedarray(napi_env, int type, size_t length, napi_value ab, size_t off, napi_value* r) {
+  if (!ab || ab->kind != K_TYPED || ab->ta_type != -1 || off + length > ab->len) return napi_invalid_arg;
+  *r = mk(K_TYPED); (*r)->ta_type = type; (*r)->len = length; (*r)->data = (char*)ab->data + off;
+  return napi_ok;
+}
 napi_status napi_delete_reference(napi_env env, napi_ref r) { delete r; env->live_refs--; return napi_ok; }
 
 // ---- helpers the Python test drives (ctypes) ---------------------------------------------------------------
@@ -174,6 +185,9 @@ void mock_set(Val* o, const char* k, Val* v) { o->props[k] = v; }
 void mock_push(Val* a, Val* v) { a->elems.push_back(v); }
 Val* mock_get(Env* e, Val* o, const char* k) { auto it = o->props.find(k); return it == o->props.end() ? &e->undef : it->second; }
 int mock_kind(Val* v) { return v->kind; }
+void* mock_typed_data(Val* v) { return v->kind == K_TYPED ? v->data : nullptr; }
+size_t mock_typed_len(Val* v) { return v->kind == K_TYPED ? v->len : 0; }
+int mock_typed_type(Val* v) { return v->kind == K_TYPED ? v->ta_type : -2; }
 double mock_number_value(Val* v) { return v->num; }
 const char* mock_string_value(Val* v) { return v->str.c_str(); }
 int mock_promise_state(Val* v) { return v->promise_state; }

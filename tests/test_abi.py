@@ -7,6 +7,7 @@ import re
 import subprocess
 import sys
 
+import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -195,3 +196,80 @@ def test_bench_reference_arm_prints_the_contract_line_with_all_host_threads():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
                           "--warmup", "0", "--gpus", "2"], capture_output=True, text=True, env=env, timeout=600)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def _png_bytes(w, h, ctype, raw_rows, extra=b""):
+    import struct
+    import zlib
+
+    def chunk(t, b):
+        return struct.pack(">I", len(b)) + t + b + struct.pack(">I", zlib.crc32(t + b) & 0xffffffff)
+    z = zlib.compress(b"".join(raw_rows))
+    half = len(z) // 2                                         # two IDAT chunks: the stream spans chunk borders
+    return b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, ctype, 0, 0, 0)) + extra + \
+        chunk(b"IDAT", z[:half]) + chunk(b"IDAT", z[half:]) + chunk(b"IEND", b""), chunk
+
+
+def _c_decode(lib, data):
+    import ctypes as C
+    w, h = C.c_int32(), C.c_int32()
+    buf = (C.c_uint8 * len(data)).from_buffer_copy(data)
+    rc = lib.rtb_decode_png(buf, len(data), C.byref(w), C.byref(h), None, 0)
+    if rc != 0:
+        return rc, None
+    out = np.zeros((h.value, w.value, 4), np.uint8)
+    rc = lib.rtb_decode_png(buf, len(data), C.byref(w), C.byref(h), out.ctypes.data, out.nbytes)
+    return rc, out
+
+
+def test_c_abi_png_decoder_matches_the_python_loadTexture_path(rt, lib):
+    """rtb_decode_png (loadTexture for C / N-API hosts, main.js:375-395) against the package's png.py on every
+    colour type and filter type, on the reference's own textures when they are at hand, and on malformed input."""
+    rng = np.random.default_rng(5)
+    w, h = 13, 11
+    for ctype, ch in ((0, 1), (2, 3), (3, 1), (4, 2), (6, 4)):
+        img = rng.integers(0, 4 if ctype == 3 else 256, (h, w * ch), dtype=np.uint8).astype(np.int32)
+        rows, prev = [], np.zeros(w * ch, np.int32)
+        for y in range(h):
+            line, ft = img[y], y % 5
+            out = np.zeros_like(line)
+            for i in range(len(line)):
+                a = line[i - ch] if i >= ch else 0
+                b = prev[i]
+                c = prev[i - ch] if i >= ch else 0
+                pa, pb, pc = abs(b - c), abs(a - c), abs(a + b - 2 * c)
+                p = [0, a, b, (a + b) >> 1, a if (pa <= pb and pa <= pc) else (b if pb <= pc else c)][ft]
+                out[i] = (line[i] - p) & 255
+            rows.append(bytes([ft]) + bytes(out.astype(np.uint8)))
+            prev = line
+        extra = b""
+        if ctype == 3:
+            _, chunk = _png_bytes(1, 1, 3, [b"\0\0"])
+            extra = chunk(b"PLTE", rng.integers(0, 256, 12, dtype=np.uint8).tobytes()) + chunk(b"tRNS", bytes([7, 200]))
+        data, _ = _png_bytes(w, h, ctype, rows, extra)
+        rc, got = _c_decode(lib, data)
+        assert rc == 0, (ctype, lib.rtb_last_error())
+        ww, hh, want = rt.png.decode_rgba8(data)
+        assert (ww, hh) == (w, h) and np.array_equal(got, want), ctype
+    # the reference's textures (present in this container only): the C decoder yields the committed texels
+    earth, mars = rt.scenes.load_planet_textures()
+    for name, tex in (("earth", earth), ("mars", mars)):
+        p = os.path.join("/root/reference", name + ".png")
+        if os.path.exists(p):
+            rc, got = _c_decode(lib, open(p, "rb").read())
+            assert rc == 0 and np.array_equal(got.reshape(-1), np.asarray(tex.texels).reshape(-1)), name
+    # malformed input: loud errors, no crash
+    import ctypes as C
+    assert _c_decode(lib, b"not a png at all")[0] != 0
+    assert _c_decode(lib, data[:40])[0] != 0                               # truncated before IDAT ends
+    bad = bytearray(data)
+    bad[24] = 16                                                           # 16-bit depth: unsupported
+    assert _c_decode(lib, bytes(bad))[0] != 0
+    w_, h_ = C.c_int32(), C.c_int32()
+    small = np.zeros(8, np.uint8)
+    buf = (C.c_uint8 * len(data)).from_buffer_copy(data)
+    assert lib.rtb_decode_png(buf, len(data), C.byref(w_), C.byref(h_), small.ctypes.data, small.nbytes) != 0
+    junk, _ = _png_bytes(w, h, 6, [b"\x09" + bytes(w * 4)] * h)            # filter type 9
+    assert _c_decode(lib, junk)[0] != 0
+    short, _ = _png_bytes(w, h, 6, [b"\x00" + bytes(w * 4)] * (h - 1))     # one scanline missing
+    assert _c_decode(lib, short)[0] != 0

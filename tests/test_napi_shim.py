@@ -36,7 +36,8 @@ def node(rt):
             ("mock_promise_state", C.c_int, [vp]), ("mock_promise_value", vp, [vp]), ("mock_live_refs", C.c_int, [vp]),
             ("mock_exception", C.c_char_p, [vp]), ("mock_clear_exception", None, [vp]),
             ("mock_load_addon", vp, [vp, C.c_char_p]), ("mock_call", vp, [vp, vp, C.c_int, C.POINTER(vp)]),
-            ("mock_run_loop", C.c_int, [vp])):
+            ("mock_run_loop", C.c_int, [vp]), ("mock_typed_data", vp, [vp]), ("mock_typed_len", C.c_size_t, [vp]),
+            ("mock_typed_type", C.c_int, [vp])):
         f = getattr(m, name)
         f.restype, f.argtypes = res, args
     env = m.mock_env_new()
@@ -102,7 +103,7 @@ def call(m, env, exports, name, *args):
 
 def test_addon_registers_and_reports_errors_as_js_exceptions(rt, node):
     m, env, exports = node
-    for name in ("render", "renderAsync", "version"):
+    for name in ("render", "renderAsync", "decodeTexture", "version"):
         assert m.mock_kind(m.mock_get(env, exports, name.encode())) == 7          # a function
     v, exc = call(m, env, exports, "version")
     assert exc is None and b"sm_100a" in m.mock_string_value(v)
@@ -123,6 +124,43 @@ def test_addon_registers_and_reports_errors_as_js_exceptions(rt, node):
     assert r is None and "texels" in exc
     r, exc = call(m, env, exports, "renderAsync", js(m, scene), js(m, bad_cam), js(m, {}), js(m, out))
     assert r is None and "projW" in exc and m.mock_live_refs(env) == 0             # nothing leaked on the error path
+
+
+def test_addon_decodes_png_textures_like_loadTexture(rt, node):
+    """decodeTexture(pngBytes): the {width, height, texels, loaded} object main.js's loadTexture leaves behind
+    (main.js:385-393), texels equal to the package's own PNG path; usable as a `textures` entry as it is."""
+    import struct
+    import zlib
+    m, env, exports = node
+
+    def chunk(t, b):
+        return struct.pack(">I", len(b)) + t + b + struct.pack(">I", zlib.crc32(t + b) & 0xffffffff)
+    rng = np.random.default_rng(9)
+    w, h = 16, 8
+    pal = rng.integers(0, 256, (5, 3), dtype=np.uint8)
+    idx = rng.integers(0, 5, (h, w), dtype=np.uint8)
+    raw = b"".join(b"\x00" + bytes(idx[y]) for y in range(h))
+    png = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 3, 0, 0, 0)) + \
+        chunk(b"PLTE", pal.tobytes()) + chunk(b"IDAT", zlib.compress(raw)) + chunk(b"IEND", b"")
+    src = np.frombuffer(png, np.uint8).copy()
+    tex, exc = call(m, env, exports, "decodeTexture", m.mock_typedarray(UINT8, src.ctypes.data, src.size))
+    assert exc is None and tex
+    assert m.mock_number_value(m.mock_get(env, tex, b"width")) == w
+    assert m.mock_number_value(m.mock_get(env, tex, b"height")) == h
+    assert m.mock_number_value(m.mock_get(env, tex, b"loaded")) == 1
+    tx = m.mock_get(env, tex, b"texels")
+    assert m.mock_typed_type(tx) == UINT8_CLAMPED and m.mock_typed_len(tx) == w * h * 4
+    got = np.ctypeslib.as_array(C.cast(m.mock_typed_data(tx), C.POINTER(C.c_uint8)), shape=(h, w, 4))
+    _, _, want = rt.png.decode_rgba8(png)
+    assert np.array_equal(got, want)
+    # errors are JS exceptions
+    r, exc = call(m, env, exports, "decodeTexture", js(m, [1, 2, 3]))
+    assert r is None and "Uint8Array" in exc
+    junk = np.arange(64, dtype=np.uint8)
+    r, exc = call(m, env, exports, "decodeTexture", m.mock_typedarray(UINT8, junk.ctypes.data, junk.size))
+    assert r is None and "PNG" in exc
+    r, exc = call(m, env, exports, "decodeTexture")
+    assert r is None and "1 argument" in exc
 
 
 def _has_gpu():
