@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <new>
 #include <vector>
 #include "rtb_internal.h"
 
@@ -53,7 +54,7 @@ extern "C" {
 // grey+alpha / RGBA - the reference's earth.png and mars.png are 8-bit palette images with PLTE only, so the
 // palette colours come back unchanged with alpha 255 (no gamma / ICC chunk, no colour management).
 int rtb_decode_png(const uint8_t* png, uint64_t len, int32_t* width, int32_t* height, uint8_t* out_rgba8,
-                   uint64_t out_capacity) {
+                   uint64_t out_capacity) try {
   static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', '\r', '\n', 0x1a, '\n'};
   if (!png || !width || !height || len < 8 || memcmp(png, sig, 8) != 0) { rtb_set_error("not a PNG"); return RTB_ERR_INVALID; }
   const uint8_t *plte = nullptr, *trns = nullptr;
@@ -133,6 +134,12 @@ int rtb_decode_png(const uint8_t* png, uint64_t len, int32_t* width, int32_t* he
     }
   }
   return RTB_OK;
+} catch (const std::bad_alloc&) {
+  rtb_set_error("PNG decoder: host allocation failed");
+  return RTB_ERR_OOM;
+} catch (...) {
+  rtb_set_error("PNG decoder: unexpected C++ exception");
+  return RTB_ERR_INVALID;
 }
 
 int rtb_look_at(const double org[3], const double tgt[3], const double up[3], int32_t width, int32_t height,
@@ -157,7 +164,7 @@ int rtb_look_at(const double org[3], const double tgt[3], const double up[3], in
   return RTB_OK;
 }
 
-int rtb_sort_spheres(RtbSphere* spheres, int32_t n, const double camera_origin[3]) {
+int rtb_sort_spheres(RtbSphere* spheres, int32_t n, const double camera_origin[3]) try {
   if (n < 0 || (n > 0 && !spheres) || !camera_origin) { rtb_set_error("bad sort arguments"); return RTB_ERR_INVALID; }
   // key = surface_area / distance3D(origin, centre), surface_area = 4 * Math.PI * r2 (main.js:160-161, 416);
   // ascending, ties keep their order (Array.prototype.sort is stable since V8 7.0)
@@ -174,6 +181,9 @@ int rtb_sort_spheres(RtbSphere* spheres, int32_t n, const double camera_origin[3
   for (int i = 0; i < n; i++) sorted[i] = spheres[key[i].second];
   std::copy(sorted.begin(), sorted.end(), spheres);
   return RTB_OK;
+} catch (const std::bad_alloc&) {
+  rtb_set_error("sort: host allocation failed");
+  return RTB_ERR_OOM;
 }
 
 // Diagnostics (host only): the packed sweep tables the wavefront kernels stage in shared memory, as built by
