@@ -67,6 +67,7 @@ def lib() -> C.CDLL:
         L.oracle_star_uniform.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
         L.oracle_star_uniform.restype = C.c_double
         L.oracle_max_threads.argtypes = []; L.oracle_max_threads.restype = C.c_int
+        L.oracle_set_libm_jitter.argtypes = [C.c_uint64, C.c_int64]; L.oracle_set_libm_jitter.restype = None
         _lib = L
     return _lib
 

@@ -12,7 +12,8 @@
  * written for this purpose; IEEE doubles via Python floats) and committing its framebuffers under
  * tests/golden/ (see oracle/gen_golden.py).  That is the reference's own source run here, but not
  * under V8: Math.atan2/asin/pow/tan come from the host libm instead of V8's fdlibm port, which can
- * differ in the last ulp.  A run under real Node (oracle/run_main_js.js) is the remaining step.
+ * differ in the last ulp (the committed frames do not move under +-2^20 ulps of such differences: see
+ * oracle_set_libm_jitter below).  A run under real Node (oracle/run_main_js.js) is the remaining step.
  *
  * Rules followed: IEEE binary64, one rounding per JS operator in source association order, no FMA
  * contraction (build with -ffp-contract=off, no -ffast-math), Math.max/min NaN-propagating,
@@ -28,6 +29,31 @@
 #include <omp.h>
 #endif
 #include "../include/rtb200.h"
+
+/* Sensitivity probe for the one open caveat above (host libm vs V8's fdlibm port, last ulp): with a non-zero
+ * seed every Math.atan2 / Math.asin / Math.pow result is moved by -max_ulps .. +max_ulps ulps, chosen by a hash of the
+ * result's bits and the seed (deterministic, thread-safe).  tests/test_oracle.py renders the golden frames
+ * with it and counts the bytes that move: a bound on what a different-but-faithful libm can change.
+ * 0 (the default) = exact libm results; nothing but that test ever sets it. */
+static uint64_t g_libm_jitter = 0;
+static int64_t g_libm_jitter_ulps = 1;
+void oracle_set_libm_jitter(uint64_t seed, int64_t max_ulps) { g_libm_jitter = seed; g_libm_jitter_ulps = max_ulps > 0 ? max_ulps : 1; }
+static inline double jitter_ulp(double r) {
+  if (g_libm_jitter == 0 || !isfinite(r)) return r;
+  uint64_t b;
+  memcpy(&b, &r, 8);
+  uint64_t h = (b ^ g_libm_jitter) * 0x9E3779B97F4A7C15ull;
+  h ^= h >> 29; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 32;
+  const int64_t k = (int64_t)(h % (uint64_t)(2 * g_libm_jitter_ulps + 1)) - g_libm_jitter_ulps;   /* -max .. +max ulps */
+  if ((b << 1) == 0) return r;                       /* +-0 stays */
+  b += (uint64_t)k;                                  /* neighbouring doubles have neighbouring bit patterns */
+  double q;
+  memcpy(&q, &b, 8);
+  return isfinite(q) && (q < 0) == (r < 0) ? q : r;
+}
+static inline double m_atan2(double y, double x) { return jitter_ulp(atan2(y, x)); }
+static inline double m_asin(double x) { return jitter_ulp(asin(x)); }
+static inline double m_pow(double x, double y) { return jitter_ulp(pow(x, y)); }
 
 typedef struct OracleCounters {
   uint64_t nodes;         /* intersectWorld calls with segs > 0                 main.js:220-221 */
@@ -143,8 +169,8 @@ static double intersectSphere(Ctx* cx, const RtbSphere* obj, const double org[3]
     normal3D(ext->n, d);
     if ((t0 < eps) || (t1 < eps)) oppose3D(ext->l, ext->n);
     else { ext->l[0] = ext->n[0]; ext->l[1] = ext->n[1]; ext->l[2] = ext->n[2]; }
-    ext->u = atan2(-ext->n[2], -ext->n[0]) / M_PI / 2 + 0.5;
-    ext->v = asin(-ext->n[1]) / (M_PI / 2) / 2 + 0.5;
+    ext->u = m_atan2(-ext->n[2], -ext->n[0]) / M_PI / 2 + 0.5;
+    ext->v = m_asin(-ext->n[1]) / (M_PI / 2) / 2 + 0.5;
     ext->m = obj;
   }
   return t;
@@ -191,8 +217,8 @@ static void sampler(Ctx* cx, const Hit* hit, uint32_t node_id, double rgb[3]) {
       sampleTexture(&cx->s->textures[m->texture_unit], hit->u, hit->v, rgb);
       return;
     case RTB_SAMPLER_CHECKER: { /* main.js:126-133 — note the axis convention differs from 446-447 */
-      const double u = atan2(-hit->n[1], -hit->n[0]) / M_PI / 2 + 0.5;
-      const double v = asin(-hit->n[2]) / (M_PI / 2) / 2 + 0.5;
+      const double u = m_atan2(-hit->n[1], -hit->n[0]) / M_PI / 2 + 0.5;
+      const double v = m_asin(-hit->n[2]) / (M_PI / 2) / 2 + 0.5;
       const int32_t s = js_toint32(u * m->checker_freq[0]) & 1;
       const int32_t t = js_toint32(v * m->checker_freq[1]) & 1;
       const double* c = m->checker_color[s ^ t];
@@ -323,7 +349,7 @@ static void intersectWorld(Ctx* cx, int segs, const double org[3], const double 
         normal3D(light_ref, light_ref);
         oppose3D(spec_dir, light_ref);
         const double spec_dot = dot3D(dir, spec_dir);
-        if (spec_dot > 0) specular_intensity += pow(spec_dot, m->specular_exponent);
+        if (spec_dot > 0) specular_intensity += m_pow(spec_dot, m->specular_exponent);
       }
     }
     diffuse_intensity = js_min(1, diffuse_intensity) * m->albedo[1];

@@ -313,6 +313,37 @@ def test_oracle_matches_main_js_golden(rt, oracle):
         assert s["within1"] == 1.0 and s["exact"] >= 0.9999, (f, s)
 
 
+def test_golden_frames_do_not_depend_on_the_last_ulps_of_libm(rt, oracle):
+    """The one open caveat of the pin: the golden frames were produced with the host libm's
+    atan2 / asin / pow / tan where V8 uses its fdlibm port; both are faithful (< 1 ulp), so they can differ by an ulp
+    or two.  Here every atan2 / asin / pow result inside the restatement is moved by up to +-4 and up to +-2^20 ulps
+    (oracle_set_libm_jitter: hash of the result's bits and a seed) and Math.tan of the projection constant
+    (main.js:105) by +-4 ulps: the main.js frames come out byte for byte the same.  So a libm that differs in the
+    last bits cannot be seen in these frames; the control at +-2^40 ulps shows that the probe is live."""
+    import math
+    L = oracle.lib()
+    sd = rt.SceneDesc(rt.scenes.demo_objects())
+    frames = {f: np.load(os.path.join(GOLDEN, f))["rgba"] for f in ("mainjs_demo_160x90.npz", "mainjs_demo_250x141.npz")}
+    try:
+        for f, gold in frames.items():
+            h, w = gold.shape[:2]
+            for seed, ulps in ((1, 4), (2, 4), (3, 1 << 20)):
+                L.oracle_set_libm_jitter(seed, ulps)
+                cam = rt.scenes.demo_camera(w, h)
+                t = math.tan(60 * math.pi / 180 / 2)
+                for _ in range(4):
+                    t = math.nextafter(t, math.inf if seed & 1 else -math.inf)
+                cam.projD = cam.projW / t
+                img, _ = oracle.render(sd, cam, rt.make_opts(segs=8))
+                assert np.array_equal(img, gold), (f, seed, ulps, int((img != gold).sum()))
+        gold = frames["mainjs_demo_160x90.npz"]
+        L.oracle_set_libm_jitter(1, 1 << 40)
+        img, _ = oracle.render(sd, rt.scenes.demo_camera(160, 90), rt.make_opts(segs=8))
+        assert (img != gold).sum() > 100                         # the probe does reach the pixels
+    finally:
+        L.oracle_set_libm_jitter(0, 1)
+
+
 def test_oracle_matches_main_js_golden_with_stars(rt, oracle):
     """Math.random as an INPUT: main.js was run with a deterministic random stream
     (gen_golden.star_stream); feeding the same stream to the restatement in the reference's call order
